@@ -1,0 +1,314 @@
+/*
+ * buddha_oracle.c -- CPU restatement of the cudabrot hot path.  TEST INFRASTRUCTURE ONLY
+ * (see buddha_oracle.h for who may call it and how its parity is pinned).
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -fPIC -shared (oracle/Makefile).
+ * -ffp-contract=off is load-bearing: every rounding below is spelled out, and fma() appears
+ * exactly where the reference's sm_100a SASS has a DFMA.
+ */
+#include "buddha_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define FMA(a, b, c) __builtin_fma((a), (b), (c))
+
+/* ---- Philox4x32-10 (curand_philox4x32_x.h:88-91,159-192) -------------------------------- */
+
+static inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  memcpy(out, c, sizeof(c));
+}
+
+/* _curand_uniform_double_hq (curand_uniform.h:101-105) then cudabrot.cu:392-393.
+ * Both multiply-adds have exact products, so the device's fused form equals this one. */
+static inline double uniform_to_coord(uint32_t x, uint32_t y) {
+  uint64_t z = (uint64_t)x ^ ((uint64_t)y << 21);
+  double u = FMA((double)z, 0x1p-53, 0x1p-54);
+  return FMA(u, 4.0, -2.0);
+}
+
+void oracle_sample(uint64_t seed, uint64_t s, double *c_real, double *c_imag) {
+  uint32_t ctr[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0u, 0u};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t o[4];
+  oracle_philox4x32_10(ctr, key, o);
+  *c_real = uniform_to_coord(o[0], o[1]);
+  *c_imag = uniform_to_coord(o[2], o[3]);
+}
+
+/* ---- canvas (cudabrot.cu:505-527) -------------------------------------------------------- */
+
+int oracle_set_deltas(oracle_dims *d) {
+  if (d->w <= 0) return 0;
+  if (d->h <= 0) return 0;
+  if (d->max_real <= d->min_real) return 0;
+  if (d->max_imag <= d->min_imag) return 0;
+  d->delta_imag = (d->max_imag - d->min_imag) / ((double)d->h);
+  d->delta_real = (d->max_real - d->min_real) / ((double)d->w);
+  return 1;
+}
+
+/* ---- rejection (cudabrot.cu:284-298) ----------------------------------------------------- */
+
+int oracle_rejected(double real, double imag) {
+  double i2 = imag * imag;              /* DMUL, shared by both tests */
+  double q0 = real - 0.25;              /* DADD */
+  double q = FMA(q0, q0, i2);           /* DFMA  :288 */
+  double lhs = q * (q0 + q);            /* DADD, DMUL :289 (q + (real-0.25) is commutative) */
+  double rhs = i2 * 0.25;               /* DMUL */
+  if (lhs < rhs) return 1;
+  double t = real + 1.0;                /* DADD :295 */
+  double b = FMA(t, t, i2);             /* DFMA :296-297 */
+  return b < 0.0625;
+}
+
+/* ---- the recurrence (cudabrot.cu:331-336 / :357-363) ------------------------------------- */
+
+#define STEP(re, im, cre, cim)                                  \
+  do {                                                          \
+    double t1_ = (im) * (im);              /* DMUL          */  \
+    double t2_ = FMA((re), (re), -t1_);    /* DFMA          */  \
+    double r2_ = (re) + (re);              /* DADD          */  \
+    double nre_ = (cre) + t2_;             /* DADD          */  \
+    (im) = FMA(r2_, (im), (cim));          /* DFMA          */  \
+    (re) = nre_;                                                \
+  } while (0)
+
+#define ESCAPED(re, im) (FMA((im), (im), (re) * (re)) > 4.0) /* DMUL, DFMA, DSETP */
+
+int oracle_escape_iterations(double c_real, double c_imag, int max_iterations) {
+  double re = c_real, im = c_imag;
+  for (int i = 0; i < max_iterations; i++) {
+    STEP(re, im, c_real, c_imag);
+    if (ESCAPED(re, im)) return i;
+  }
+  return max_iterations;
+}
+
+int oracle_cycle_detect_iterations(double c_real, double c_imag, int max_iterations, int stride) {
+  double re = c_real, im = c_imag;
+  double ref_re = re, ref_im = im;
+  if (stride < 1) stride = 1;
+  int next_ckpt = stride;
+  for (int i = 0; i < max_iterations; i++) {
+    STEP(re, im, c_real, c_imag);
+    if (ESCAPED(re, im)) return -1;
+    int n = i + 1; /* iterations done */
+    if (n % stride == 0) {
+      if (memcmp(&re, &ref_re, 8) == 0 && memcmp(&im, &ref_im, 8) == 0) return n;
+      if (n == next_ckpt) { ref_re = re; ref_im = im; next_ckpt *= 2; }
+    }
+  }
+  return -1;
+}
+
+/* cvt.rzi.s32.f64: truncate toward zero, saturate, NaN -> 0 (host (int) is UB out of range). */
+static inline int32_t sat_trunc_i32(double v) {
+  if (v != v) return 0;
+  if (v >= 2147483648.0) return INT32_MAX;
+  if (v <= -2147483649.0) return INT32_MIN;
+  return (int32_t)v;
+}
+
+/* IncrementPixelCounter, cudabrot.cu:302-314.  Returns 1 if a cell was incremented. */
+static inline int bin_point(double re, double im, const oracle_dims *d, int64_t *index) {
+  if ((re < d->min_real) || (im < d->min_imag)) return 0;
+  int32_t col = sat_trunc_i32((re - d->min_real) / d->delta_real);
+  int32_t row = sat_trunc_i32((im - d->min_imag) / d->delta_imag);
+  if ((row >= 0) && (row < d->h) && (col >= 0) && (col < d->w)) {
+    *index = (int64_t)((int32_t)(row * d->w) + col); /* 32-bit int index, :312 */
+    return 1;
+  }
+  return 0;
+}
+
+typedef struct {
+  uint32_t *hist;
+  int atomic;
+} sink_t;
+
+static inline void sink_add(sink_t *s, int64_t idx) {
+  if (s->atomic) {
+#pragma omp atomic
+    s->hist[idx] += 1u;
+  } else {
+    s->hist[idx] += 1u;
+  }
+}
+
+static void render_range(const oracle_dims *d, int max_it, int min_it, uint64_t seed,
+                         uint64_t first, uint64_t count, sink_t *sink, oracle_counters *c) {
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    c->candidates++;
+    if (oracle_rejected(cre, cim)) { c->rejected++; continue; }
+    int i = oracle_escape_iterations(cre, cim, max_it);
+    if (i >= max_it) { c->hit_max++; c->escape_iters += (uint64_t)(max_it > 0 ? max_it : 0); continue; }
+    c->escape_iters += (uint64_t)i + 1u;
+    if (i < min_it) { c->too_early++; continue; }
+    c->accepted++;
+    /* IterateAndRecord, cudabrot.cu:347-365 */
+    double re = cre, im = cim;
+    for (;;) {
+      STEP(re, im, cre, cim);
+      c->orbit_points++;
+      int64_t idx;
+      if (bin_point(re, im, d, &idx)) { sink_add(sink, idx); c->increments++; }
+      if (ESCAPED(re, im)) break;
+    }
+  }
+}
+
+static void counters_add(oracle_counters *a, const oracle_counters *b) {
+  a->candidates += b->candidates; a->rejected += b->rejected; a->hit_max += b->hit_max;
+  a->too_early += b->too_early; a->accepted += b->accepted; a->escape_iters += b->escape_iters;
+  a->orbit_points += b->orbit_points; a->increments += b->increments;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, uint64_t seed,
+                  uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
+                  int threads) {
+  int nt = threads > 0 ? threads : oracle_max_threads();
+  size_t cells = (size_t)d->w * (size_t)d->h;
+  oracle_counters total;
+  memset(&total, 0, sizeof(total));
+  /* private histograms while they stay under ~2 GiB in total, shared + omp atomic beyond */
+  int use_private = (nt > 1) && (cells * 4u * (size_t)nt <= ((size_t)2 << 30));
+  const uint64_t chunk = 4096;
+  uint64_t nchunks = (count + chunk - 1) / chunk;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt)
+#endif
+  {
+    oracle_counters local;
+    memset(&local, 0, sizeof(local));
+    sink_t sink;
+    sink.hist = hist;
+    sink.atomic = (nt > 1) && !use_private;
+    uint32_t *priv = NULL;
+    if (use_private) {
+      priv = (uint32_t *)calloc(cells, sizeof(uint32_t));
+      if (priv) { sink.hist = priv; sink.atomic = 0; } else { sink.atomic = 1; }
+    }
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (uint64_t ci = 0; ci < nchunks; ci++) {
+      uint64_t lo = ci * chunk;
+      uint64_t n = (count - lo < chunk) ? (count - lo) : chunk;
+      render_range(d, max_iterations, min_iterations, seed, first + lo, n, &sink, &local);
+    }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+    {
+      counters_add(&total, &local);
+      if (priv) {
+        for (size_t p = 0; p < cells; p++) hist[p] += priv[p];
+      }
+    }
+    free(priv);
+  }
+  if (counters) *counters = total;
+  return nt;
+}
+
+void oracle_classify(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                     int32_t *out_iters) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    out_iters[k] = oracle_rejected(cre, cim) ? -1
+                                             : oracle_escape_iterations(cre, cim, max_iterations);
+  }
+}
+
+/* ---- tone-map (cudabrot.cu:416-468), host arithmetic: no FMA, glibc pow ------------------ */
+
+static inline uint16_t clamp_u16(double v) { /* Clamp, :416-420 */
+  if (v <= 0) return 0;
+  if (v >= 0xffff) return 0xffff;
+  return (uint16_t)v;
+}
+
+/* (uint16_t) of a double as x86-64 gcc does it: cvttsd2si to 32 bits, keep the low 16.
+ * NaN / out of range -> 0x80000000 -> 0.  Spelled out so the oracle has no UB. */
+static inline uint16_t x86_double_to_u16(double v) {
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;
+  return (uint16_t)(uint32_t)(int32_t)v;
+}
+
+void oracle_tonemap(const uint32_t *hist, size_t cells, double gamma, int big_endian,
+                    uint16_t *out, uint32_t *max_out, double *scale_out) {
+  uint32_t max = 0;
+  for (size_t p = 0; p < cells; p++) if (hist[p] > max) max = hist[p]; /* :430-435 */
+  double scale = ((double)0xffff) / ((double)max);                     /* :436 */
+  if (max_out) *max_out = max;
+  if (scale_out) *scale_out = scale;
+  const double m = 0xffff;
+  for (size_t p = 0; p < cells; p++) {
+    double scaled = ((double)hist[p]) * scale;                         /* :445 */
+    uint16_t v;
+    if (gamma <= 0.0) {
+      v = x86_double_to_u16(scaled);                                   /* :447 */
+    } else {
+      double g = m * pow(scaled / m, 1 / gamma);                       /* :448 */
+      v = (g != g) ? x86_double_to_u16(g) : clamp_u16(g);
+    }
+    if (big_endian) v = (uint16_t)(((v & 0xff) << 8) | (v >> 8));      /* :568 */
+    out[p] = v;
+  }
+}
+
+int oracle_write_pgm(const char *path, const uint16_t *image, int w, int h) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return 1;
+  if (fprintf(f, "P5\n%d %d\n%d\n", w, h, 0xffff) <= 0) { fclose(f); return 2; }
+  size_t n = (size_t)w * (size_t)h;
+  uint16_t *tmp = (uint16_t *)malloc(n * 2);
+  if (!tmp) { fclose(f); return 3; }
+  for (size_t i = 0; i < n; i++) tmp[i] = (uint16_t)(((image[i] & 0xff) << 8) | (image[i] >> 8));
+  int ok = fwrite(tmp, n * 2, 1, f) == 1;
+  free(tmp);
+  fclose(f);
+  return ok ? 0 : 4;
+}
+
+uint64_t oracle_fnv1a64(const uint32_t *data, size_t cells) {
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  const uint8_t *b = (const uint8_t *)data;
+  for (size_t i = 0; i < cells * 4; i++) { hsh ^= b[i]; hsh *= 0x100000001b3ull; }
+  return hsh;
+}

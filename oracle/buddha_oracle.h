@@ -1,0 +1,94 @@
+/*
+ * buddha_oracle.h -- CPU restatement of the cudabrot hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is the checker, never the product: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product path (cudabrot_b200/csrc) never
+ * links or calls anything in oracle/.
+ *
+ * Parity status: the reference (/root/reference/cudabrot.cu) ships no tests, golden vectors or
+ * CPU path, so parity is pinned by
+ *   (1) Random123 Philox4x32-10 known-answer vectors (tests/test_oracle.py),
+ *   (2) the reference's own device functions executed on a B200 over this oracle's sample list
+ *       (oracle/ref_probe.cu includes the reference source where it lies; `-m gpu` test), and
+ *   (3) the reference's own host tone-map/PGM code executed here on the CPU (same ref_probe binary),
+ *       with the outputs committed under tests/golden/.
+ */
+#ifndef BUDDHA_ORACLE_H
+#define BUDDHA_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors FractalDimensions, cudabrot.cu:46-58 (same field order, 56 bytes). */
+typedef struct {
+  int32_t w, h;
+  double min_real, min_imag, max_real, max_imag;
+  double delta_real, delta_imag;
+} oracle_dims;
+
+/* Work counters: S, E, P, I and the classification of every candidate. */
+typedef struct {
+  uint64_t candidates;   /* S: every drawn c, including rejected ones                         */
+  uint64_t rejected;     /* in main cardioid or period-2 bulb (cudabrot.cu:398)               */
+  uint64_t hit_max;      /* ran max iterations without escaping (cudabrot.cu:407)             */
+  uint64_t too_early;    /* escaped with i < min (cudabrot.cu:408)                            */
+  uint64_t accepted;     /* min <= i < max                                                    */
+  uint64_t escape_iters; /* E: iterations IterateMandelbrot executes (i+1, or max)            */
+  uint64_t orbit_points; /* P: sum of (i+1) over accepted samples                             */
+  uint64_t increments;   /* I: orbit points that landed inside the canvas                     */
+} oracle_counters;
+
+/* Philox4x32-10, /usr/local/cuda/include/curand_philox4x32_x.h:88-91,159-192. */
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Sample index s -> candidate c (replaces cudabrot.cu:392-393 with the stateless Philox stream). */
+void oracle_sample(uint64_t seed, uint64_t s, double *c_real, double *c_imag);
+
+/* RecomputePixelDeltas, cudabrot.cu:505-527.  Returns 1 if valid (deltas filled in), else 0. */
+int oracle_set_deltas(oracle_dims *d);
+
+/* InMainCardioid || InOrder2Bulb, cudabrot.cu:284-298 (SASS dataflow). */
+int oracle_rejected(double real, double imag);
+
+/* IterateMandelbrot, cudabrot.cu:319-340. */
+int oracle_escape_iterations(double c_real, double c_imag, int max_iterations);
+
+/* First bit-exact repeat of z (orbit provably periodic in this arithmetic): returns the iteration
+ * index at which Brent's algorithm sees z == checkpoint, or -1 if none within max_iterations.
+ * Used only to study / test the product's exact non-escape shortcut. */
+int oracle_cycle_detect_iterations(double c_real, double c_imag, int max_iterations, int stride);
+
+/* DrawBuddhabrot over samples [first, first+count), race-free (every increment counts).
+ * hist is uint32[h*w], accumulated into (not cleared).  threads<=0 -> omp_get_max_threads().
+ * Returns the number of OpenMP threads actually used. */
+int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, uint64_t seed,
+                  uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
+                  int threads);
+
+/* Escape classification only (no histogram): out_iters[k] = IterateMandelbrot result for sample
+ * first+k, or -1 if rejected by the cardioid/bulb test. */
+void oracle_classify(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                     int32_t *out_iters);
+
+/* SetGrayscalePixels + GetLinearColorScale + DoGammaCorrection + Clamp, cudabrot.cu:416-468.
+ * big_endian!=0 additionally applies SaveImage's byte swap (cudabrot.cu:566-570). */
+void oracle_tonemap(const uint32_t *hist, size_t cells, double gamma, int big_endian,
+                    uint16_t *out, uint32_t *max_out, double *scale_out);
+
+/* SaveImage, cudabrot.cu:548-577: "P5\n<w> <h>\n65535\n" + big-endian pixels.  image is
+ * host-endian on entry (not modified).  Returns 0 on success. */
+int oracle_write_pgm(const char *path, const uint16_t *image, int w, int h);
+
+/* FNV-1a-64 over the little-endian bytes of a uint32 array (the survey's histogram digest). */
+uint64_t oracle_fnv1a64(const uint32_t *data, size_t cells);
+
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,152 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU checker (test infrastructure only).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package (cudabrot_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+REF_PROBE = os.path.join(REF_DIR, "ref_probe")
+REF_BINARY = os.path.join(REF_DIR, "cudabrot_ref")
+
+
+class Dims(C.Structure):
+    """FractalDimensions, cudabrot.cu:46-58."""
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32),
+                ("min_real", C.c_double), ("min_imag", C.c_double),
+                ("max_real", C.c_double), ("max_imag", C.c_double),
+                ("delta_real", C.c_double), ("delta_imag", C.c_double)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("candidates", "rejected", "hit_max", "too_early", "accepted",
+                 "escape_iters", "orbit_points", "increments")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(ORACLE_DIR, "buddha_oracle.c")):
+        subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        u32p, i32p, u16p = (C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint16))
+        L.oracle_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.oracle_sample.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.oracle_set_deltas.argtypes = [C.POINTER(Dims)]
+        L.oracle_set_deltas.restype = C.c_int
+        L.oracle_rejected.argtypes = [C.c_double, C.c_double]
+        L.oracle_rejected.restype = C.c_int
+        L.oracle_escape_iterations.argtypes = [C.c_double, C.c_double, C.c_int]
+        L.oracle_escape_iterations.restype = C.c_int
+        L.oracle_cycle_detect_iterations.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        L.oracle_cycle_detect_iterations.restype = C.c_int
+        L.oracle_render.argtypes = [C.POINTER(Dims), C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                    C.c_uint64, u32p, C.POINTER(Counters), C.c_int]
+        L.oracle_render.restype = C.c_int
+        L.oracle_classify.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, i32p]
+        L.oracle_tonemap.argtypes = [u32p, C.c_size_t, C.c_double, C.c_int, u16p, u32p,
+                                     C.POINTER(C.c_double)]
+        L.oracle_write_pgm.argtypes = [C.c_char_p, u16p, C.c_int, C.c_int]
+        L.oracle_write_pgm.restype = C.c_int
+        L.oracle_fnv1a64.argtypes = [u32p, C.c_size_t]
+        L.oracle_fnv1a64.restype = C.c_uint64
+        L.oracle_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def philox(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().oracle_philox4x32_10(_p(c, C.c_uint32), _p(k, C.c_uint32), _p(o, C.c_uint32))
+    return o
+
+
+def sample(seed, s):
+    re, im = C.c_double(), C.c_double()
+    lib().oracle_sample(seed, s, C.byref(re), C.byref(im))
+    return re.value, im.value
+
+
+def samples(seed, first, count):
+    out = np.empty((count, 2), dtype=np.float64)
+    for k in range(count):
+        out[k] = sample(seed, first + k)
+    return out
+
+
+def make_dims(w, h, min_real=-2.0, max_real=2.0, min_imag=-2.0, max_imag=2.0):
+    d = Dims(w, h, min_real, min_imag, max_real, max_imag, 0.0, 0.0)
+    if not lib().oracle_set_deltas(C.byref(d)):
+        raise ValueError("invalid canvas")
+    return d
+
+
+def render(w, h, max_iter, min_iter, seed, first, count, canvas=(-2.0, 2.0, -2.0, 2.0),
+           hist=None, threads=0):
+    """Returns (hist uint32[h,w], counters dict, threads used)."""
+    d = make_dims(w, h, *canvas)
+    if hist is None:
+        hist = np.zeros((h, w), dtype=np.uint32)
+    cnt = Counters()
+    nt = lib().oracle_render(C.byref(d), max_iter, min_iter, seed, first, count,
+                             _p(hist, C.c_uint32), C.byref(cnt), threads)
+    return hist, cnt.as_dict(), nt
+
+
+def classify(seed, first, count, max_iter):
+    out = np.empty(count, dtype=np.int32)
+    lib().oracle_classify(seed, first, count, max_iter, _p(out, C.c_int32))
+    return out
+
+
+def tonemap(hist, gamma, big_endian=False):
+    """Returns (uint16 image (same shape), max, scale)."""
+    h = np.ascontiguousarray(hist, dtype=np.uint32)
+    out = np.empty(h.shape, dtype=np.uint16)
+    mx, sc = C.c_uint32(), C.c_double()
+    lib().oracle_tonemap(_p(h, C.c_uint32), h.size, gamma, int(big_endian), _p(out, C.c_uint16),
+                         C.byref(mx), C.byref(sc))
+    return out, mx.value, sc.value
+
+
+def write_pgm(path, image):
+    img = np.ascontiguousarray(image, dtype=np.uint16)
+    rc = lib().oracle_write_pgm(path.encode(), _p(img, C.c_uint16), img.shape[1], img.shape[0])
+    if rc:
+        raise OSError("oracle_write_pgm failed: %d" % rc)
+
+
+def fnv1a64(hist):
+    h = np.ascontiguousarray(hist, dtype=np.uint32)
+    return int(lib().oracle_fnv1a64(_p(h, C.c_uint32), h.size))
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
