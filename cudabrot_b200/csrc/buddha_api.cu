@@ -1,0 +1,632 @@
+// buddha_api.cu -- host side of libbuddha.so: the C ABI declared in include/buddha.h.
+//
+// Each export cites the reference call site it replaces in include/buddha.h.  This file owns the
+// device memory, the stream and the launch policy; the kernels are in buddha_kernels.cuh.
+// There is no CPU fallback anywhere in this library.
+#include "../../include/buddha.h"
+#include "buddha_kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <vector>
+
+using namespace buddha;
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+constexpr uint32_t kLutMax = 1u << 22;  // counts below this are tone-mapped through a full table
+
+struct FastBin {
+  double inv_half, c0_lo, c0_hi;
+  bool ok;
+};
+
+}  // namespace
+
+struct buddha_ctx {
+  buddha_params params;
+  double delta_re, delta_im;
+  size_t cells;
+  int sm_count;
+  int grid;                       // persistent grid: resident CTAs per SM x SMs
+  cudaStream_t stream;
+  cudaEvent_t ev_a, ev_b, ev_ta, ev_tb;
+  uint32_t *d_hist;
+  unsigned long long *d_cursor;   // offset handed out so far in the current launch
+  unsigned long long *d_counters; // kCntSlots accumulators
+  uint32_t *d_max;
+  uint16_t *d_gray;               // tone-mapped image, allocated on first use
+  uint16_t *d_lut;
+  uint32_t *d_thr;
+  uint32_t lut_capacity;
+  RenderParams rp;
+  uint64_t candidates;            // host tally: every index in a rendered range is a candidate
+  uint64_t launches;
+  bool render_timed, tonemap_timed;
+  char err[512];
+};
+
+namespace {
+
+int fail(buddha_ctx *ctx, int code, const char *fmt, ...) {
+  char *dst = ctx ? ctx->err : g_create_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(ctx, call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail((ctx), BUDDHA_ECUDA, "CUDA error %d (%s) in %s, line %d (%s)", (int)e_,   \
+                  cudaGetErrorString(e_), __FILE__, __LINE__, #call);                       \
+  } while (0)
+
+// Constants of the division-free binning for one axis (see bin_point and DESIGN.md section 4).
+// T = fma(X, inv_half, c0) = (X/2 - min) * inv + 1.5*2^40 +- 2^-11, rounded onto the 2^-12 grid.
+FastBin make_fast_bin(double min_v, double delta, int n) {
+  FastBin f;
+  f.ok = false;
+  f.inv_half = f.c0_lo = f.c0_hi = 0.0;
+  double inv = 1.0 / delta;
+  if (!(inv > 0.0) || !isfinite(inv)) return f;
+  if (n > (1 << 19)) return f;                       // quotient must stay below 2^20
+  if (!(fabs(min_v) * inv < 0x1p36)) return f;       // keeps |c0| in the 2^40 binade, errors < 2^-12
+  long double base = (long double)0x1.8p40 - (long double)min_v * (long double)inv;
+  f.c0_hi = (double)(base + (long double)0x1p-11);
+  f.c0_lo = (double)(base - (long double)0x1p-11);
+  f.inv_half = inv * 0.5;
+  f.ok = true;
+  return f;
+}
+
+void fill_render_params(buddha_ctx *c) {
+  const buddha_params &p = c->params;
+  RenderParams &r = c->rp;
+  memset(&r, 0, sizeof(r));
+  r.w = p.width; r.h = p.height;
+  r.min_re = p.min_real; r.min_im = p.min_imag;
+  r.delta_re = c->delta_re; r.delta_im = c->delta_im;
+  FastBin fr = make_fast_bin(p.min_real, c->delta_re, p.width);
+  FastBin fi = make_fast_bin(p.min_imag, c->delta_im, p.height);
+  r.fast_bin = (fr.ok && fi.ok && !(p.flags & BUDDHA_F_EXACT_BINNING)) ? 1 : 0;
+  r.inv_half_re = fr.inv_half; r.c0_lo_re = fr.c0_lo; r.c0_hi_re = fr.c0_hi;
+  r.inv_half_im = fi.inv_half; r.c0_lo_im = fi.c0_lo; r.c0_hi_im = fi.c0_hi;
+  r.max_it = p.max_iterations; r.min_it = p.min_iterations;
+  r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
+  uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  for (int i = 0; i < 10; i++) {
+    r.key0[i] = k0; r.key1[i] = k1;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+double now_seconds() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + (double)ts.tv_nsec / 1e9;
+}
+
+// ---- the reference's tone-map expression, evaluated on the host for one count ---------------
+// DoGammaCorrection + Clamp (cudabrot.cu:443-449, :416-420).  Same operations in the same order,
+// each individually rounded (this TU is compiled with -ffp-contract=off and no FMA ISA), and the
+// same libm pow the reference would call on this machine.
+
+inline uint16_t double_to_u16_like_x86(double v) {
+  // (uint16_t) of a double on x86-64: cvttsd2si to 32 bits, keep the low half; NaN -> 0.
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;
+  return (uint16_t)(uint32_t)(int32_t)v;
+}
+
+inline uint16_t tone_value(uint32_t count, double scale, double gamma) {
+  const double top = 0xffff;
+  double scaled = ((double)count) * scale;
+  if (gamma <= 0.0) return double_to_u16_like_x86(scaled);
+  double v = top * pow(scaled / top, 1 / gamma);
+  if (v != v) return 0;
+  if (v <= 0) return 0;
+  if (v >= 0xffff) return 0xffff;
+  return (uint16_t)v;
+}
+
+inline uint16_t bswap16(uint16_t v) { return (uint16_t)((v << 8) | (v >> 8)); }
+
+// ---- NCCL, loaded lazily -----------------------------------------------------------------------
+
+struct NcclApi {
+  void *lib;
+  int (*CommInitAll)(void **, int, const int *);
+  int (*CommDestroy)(void *);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t);
+  const char *(*GetErrorString)(int);
+};
+
+NcclApi *load_nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return nullptr;
+  api.CommInitAll = (int (*)(void **, int, const int *))dlsym(api.lib, "ncclCommInitAll");
+  api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+  api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+  api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
+  api.Reduce = (int (*)(const void *, void *, size_t, int, int, int, void *, cudaStream_t))
+      dlsym(api.lib, "ncclReduce");
+  api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.CommInitAll || !api.CommDestroy || !api.GroupStart || !api.GroupEnd || !api.Reduce) {
+    dlclose(api.lib);
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+uint32_t buddha_abi_version(void) { return BUDDHA_ABI_VERSION; }
+
+void buddha_default_params(buddha_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->struct_size = sizeof(*p);
+  p->device = 0;
+  p->width = 1000; p->height = 1000;
+  p->min_real = -2.0; p->max_real = 2.0; p->min_imag = -2.0; p->max_imag = 2.0;
+  p->max_iterations = 100; p->min_iterations = 20;
+  p->seed = 1337;
+}
+
+int buddha_validate_canvas(const buddha_params *p, double *delta_real, double *delta_imag,
+                           const char **why) {
+  const char *msg = nullptr;
+  // same rules, same order, same messages as cudabrot.cu:505-523 (the last one is worded
+  // backwards in the reference; kept so scripts that grep the output keep working)
+  if (p->width <= 0) msg = "Output width must be positive.";
+  else if (p->height <= 0) msg = "Output height must be positive.";
+  else if (p->max_real <= p->min_real)
+    msg = "Maximum real value must be greater than minimum real value.";
+  else if (p->max_imag <= p->min_imag)
+    msg = "Minimum imaginary value must be greater than maximum imaginary value.";
+  if (why) *why = msg;
+  if (msg) return BUDDHA_EINVAL;
+  if (delta_imag) *delta_imag = (p->max_imag - p->min_imag) / ((double)p->height);
+  if (delta_real) *delta_real = (p->max_real - p->min_real) / ((double)p->width);
+  return BUDDHA_OK;
+}
+
+const char *buddha_last_error(const buddha_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int buddha_create(buddha_ctx **out, const buddha_params *p) {
+  if (!out || !p) return fail(nullptr, BUDDHA_EINVAL, "null argument");
+  *out = nullptr;
+  if (p->struct_size != sizeof(buddha_params))
+    return fail(nullptr, BUDDHA_EINVAL, "buddha_params.struct_size %u != %zu", p->struct_size,
+                sizeof(buddha_params));
+  const char *why = nullptr;
+  double dre = 0, dim = 0;
+  if (buddha_validate_canvas(p, &dre, &dim, &why)) return fail(nullptr, BUDDHA_EINVAL, "%s", why);
+  // the reference indexes pixels with 32-bit int (cudabrot.cu:312, :551)
+  if ((uint64_t)p->width * (uint64_t)p->height > 0x7fffffffull)
+    return fail(nullptr, BUDDHA_EINVAL, "width*height exceeds 2^31-1 cells");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, BUDDHA_ENODEV, "no CUDA device: %s (libbuddha has no CPU fallback)",
+                cudaGetErrorString(e));
+  if (p->device < 0 || p->device >= ndev)
+    return fail(nullptr, BUDDHA_EINVAL, "device %d out of range (%d devices)", p->device, ndev);
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major != 10)
+    return fail(nullptr, BUDDHA_ENODEV, "device %d is sm_%d%d; libbuddha is built for sm_100a only",
+                p->device, prop.major, prop.minor);
+  CU(nullptr, cudaSetDevice(p->device));
+
+  buddha_ctx *c = (buddha_ctx *)calloc(1, sizeof(buddha_ctx));
+  if (!c) return fail(nullptr, BUDDHA_ENOMEM, "out of host memory");
+  c->params = *p;
+  c->delta_re = dre; c->delta_im = dim;
+  c->cells = (size_t)p->width * (size_t)p->height;
+  c->sm_count = prop.multiProcessorCount;
+  fill_render_params(c);
+
+  int per_sm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel,
+                                                                 kThreadsPerCta, 0);
+  if (st != cudaSuccess || per_sm < 1) {
+    free(c);
+    return fail(nullptr, BUDDHA_ECUDA, "render kernel not launchable on device %d: %s", p->device,
+                cudaGetErrorString(st));
+  }
+  c->grid = per_sm * c->sm_count;
+
+#define CUC(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      fail(nullptr, e_ == cudaErrorMemoryAllocation ? BUDDHA_ENOMEM : BUDDHA_ECUDA,          \
+           "CUDA error %d (%s) in %s, line %d (%s)", (int)e_, cudaGetErrorString(e_),        \
+           __FILE__, __LINE__, #call);                                                       \
+      buddha_destroy(c);                                                                     \
+      return e_ == cudaErrorMemoryAllocation ? BUDDHA_ENOMEM : BUDDHA_ECUDA;                 \
+    }                                                                                        \
+  } while (0)
+  CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreate(&c->ev_a));
+  CUC(cudaEventCreate(&c->ev_b));
+  CUC(cudaEventCreate(&c->ev_ta));
+  CUC(cudaEventCreate(&c->ev_tb));
+  CUC(cudaMalloc(&c->d_hist, c->cells * sizeof(uint32_t)));
+  CUC(cudaMemsetAsync(c->d_hist, 0, c->cells * sizeof(uint32_t), c->stream));
+  CUC(cudaMalloc(&c->d_cursor, sizeof(unsigned long long)));
+  CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCntSlots));
+  CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
+  CUC(cudaMalloc(&c->d_max, sizeof(uint32_t)));
+  CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
+  CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+  *out = c;
+  return BUDDHA_OK;
+}
+
+void buddha_destroy(buddha_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->params.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters); cudaFree(c->d_max);
+  cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_ta) cudaEventDestroy(c->ev_ta);
+  if (c->ev_tb) cudaEventDestroy(c->ev_tb);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  free(c);
+}
+
+int buddha_clear_histogram(buddha_ctx *c) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemsetAsync(c->d_hist, 0, c->cells * sizeof(uint32_t), c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_load_histogram(buddha_ctx *c, const uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "histogram has %zu cells, canvas needs %zu", cells, c->cells);
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemcpyAsync(c->d_hist, host, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, canvas has %zu", cells, c->cells);
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemcpyAsync(host, c->d_hist, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
+  if (count == 0) return BUDDHA_OK;
+  if (first + count < first) return fail(c, BUDDHA_EINVAL, "sample range wraps around 2^64");
+  RenderParams rp = c->rp;
+  rp.end = first + count;
+  if (c->params.flags & BUDDHA_F_SIMPLE_KERNEL) {
+    uint64_t want = (count + 255) / 256;
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)c->sm_count * 32);
+    render_simple_kernel<<<grid, 256, 0, c->stream>>>(rp, first, c->d_hist, c->d_counters);
+  } else {
+    // the cursor starts at `first`; warps take kChunk indices at a time until it passes rp.end
+    unsigned long long start = first;
+    CU(c, cudaMemcpyAsync(c->d_cursor, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
+    uint64_t want = (count + kChunk - 1) / kChunk;  // warps that can get work at all
+    uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
+    int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
+    render_persistent_kernel<<<grid, kThreadsPerCta, 0, c->stream>>>(rp, c->d_hist, c->d_cursor,
+                                                                      c->d_counters);
+  }
+  CU(c, cudaGetLastError());
+  c->candidates += count;
+  c->launches += 1;
+  return BUDDHA_OK;
+}
+
+int buddha_render_samples_async(buddha_ctx *c, uint64_t first, uint64_t count) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaEventRecord(c->ev_a, c->stream));
+  int rc = enqueue_render(c, first, count);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev_b, c->stream));
+  c->render_timed = true;
+  return BUDDHA_OK;
+}
+
+int buddha_sync(buddha_ctx *c) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_render_samples(buddha_ctx *c, uint64_t first, uint64_t count) {
+  int rc = buddha_render_samples_async(c, first, count);
+  if (rc) return rc;
+  return buddha_sync(c);
+}
+
+int buddha_render_seconds(buddha_ctx *c, double seconds, volatile int *stop, uint64_t first,
+                          uint64_t *samples_done, uint64_t *passes) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  uint64_t done = 0, npass = 0;
+  // first pass = one reference pass (512*512*50 candidates, cudabrot.cu:20,23,34); later passes
+  // are sized for ~0.1 s so the stop flag / deadline latency stays bounded at any -m
+  uint64_t pass = 13107200ull;
+  double t0 = now_seconds();
+  CU(c, cudaEventRecord(c->ev_a, c->stream));
+  while (!(stop && *stop)) {
+    double ta = now_seconds();
+    int rc = enqueue_render(c, first + done, pass);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    double tb = now_seconds();
+    done += pass;
+    npass++;
+    if ((seconds >= 0) && ((tb - t0) > seconds)) break;
+    double rate = (double)pass / std::max(tb - ta, 1e-6);
+    double next = rate * 0.1;
+    if (seconds >= 0) next = std::min(next, rate * std::max(seconds - (tb - t0), 0.005));
+    uint64_t n = (uint64_t)std::min(std::max(next, 1048576.0), 68719476736.0);
+    pass = (n + kChunk - 1) / kChunk * kChunk;
+  }
+  CU(c, cudaEventRecord(c->ev_b, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->render_timed = true;
+  if (samples_done) *samples_done = done;
+  if (passes) *passes = npass;
+  return BUDDHA_OK;
+}
+
+int buddha_last_render_ms(buddha_ctx *c, float *ms) {
+  if (!c || !ms) return BUDDHA_EINVAL;
+  if (!c->render_timed) return fail(c, BUDDHA_EINVAL, "no render call has been timed yet");
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaEventSynchronize(c->ev_b));
+  CU(c, cudaEventElapsedTime(ms, c->ev_a, c->ev_b));
+  return BUDDHA_OK;
+}
+
+int buddha_get_counters(buddha_ctx *c, buddha_counters *out) {
+  if (!c || !out) return BUDDHA_EINVAL;
+  unsigned long long v[kCntSlots];
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemcpyAsync(v, c->d_counters, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  memset(out, 0, sizeof(*out));
+  out->candidates = c->candidates;
+  out->rejected = v[kCntRejected];
+  out->hit_max = v[kCntHitMax];
+  out->too_early = v[kCntTooEarly];
+  out->accepted = v[kCntAccepted];
+  out->escape_iters = v[kCntEscapeIters];
+  out->orbit_points = v[kCntOrbitPoints];
+  out->increments = v[kCntIncrements];
+  out->executed_iters = v[kCntExecuted];
+  out->shortcut_hits = v[kCntShortcut];
+  out->exact_bins = v[kCntExactBins];
+  out->kernel_launches = c->launches;
+  return BUDDHA_OK;
+}
+
+int buddha_reset_counters(buddha_ctx *c) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->candidates = 0;
+  c->launches = 0;
+  return BUDDHA_OK;
+}
+
+int buddha_tonemap_u16(buddha_ctx *c, double gamma, int big_endian, uint16_t *host_out,
+                       size_t cells, uint32_t *max_out, double *scale_out) {
+  if (!c) return BUDDHA_EINVAL;
+  if (host_out && cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->cells);
+  CU(c, cudaSetDevice(c->params.device));
+  const int blocks = c->sm_count * 8;
+
+  // pass 1: GetLinearColorScale's maximum (cudabrot.cu:430-435)
+  CU(c, cudaEventRecord(c->ev_ta, c->stream));
+  CU(c, cudaMemsetAsync(c->d_max, 0, sizeof(uint32_t), c->stream));
+  hist_max_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hist, c->cells, c->d_max);
+  CU(c, cudaGetLastError());
+  c->launches += 1;
+  uint32_t mx = 0;
+  CU(c, cudaMemcpyAsync(&mx, c->d_max, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  double scale = ((double)0xffff) / ((double)mx);  // :436 (inf when the histogram is empty)
+  if (max_out) *max_out = mx;
+  if (scale_out) *scale_out = scale;
+  if (!host_out) {
+    CU(c, cudaEventRecord(c->ev_tb, c->stream));
+    c->tonemap_timed = true;
+    return BUDDHA_OK;
+  }
+
+  // host: tabulate the reference's count -> grey expression (glibc pow and all)
+  uint32_t lut_size = (mx < kLutMax) ? (mx + 1) : kLutMax;
+  std::vector<uint16_t> lut(lut_size);
+#pragma omp parallel for schedule(static)
+  for (long long k = 0; k < (long long)lut_size; k++) {
+    uint16_t v = tone_value((uint32_t)k, scale, gamma);
+    lut[k] = big_endian ? bswap16(v) : v;
+  }
+  if (lut_size > c->lut_capacity) {
+    cudaFree(c->d_lut);
+    c->d_lut = nullptr;
+    c->lut_capacity = 0;
+    CU(c, cudaMalloc(&c->d_lut, sizeof(uint16_t) * (size_t)lut_size));
+    c->lut_capacity = lut_size;
+  }
+  CU(c, cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * (size_t)lut_size,
+                        cudaMemcpyHostToDevice, c->stream));
+  if (mx >= lut_size) {
+    // counts past the table: thr[v] = smallest count in [0, mx] whose value is >= v, found by
+    // bisection on the (monotone) reference expression; mx + 1 if no count reaches v
+    std::vector<uint32_t> thr(65536);
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < 65536; v++) {
+      uint64_t lo = 0, hi = (uint64_t)mx + 1;
+      while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (tone_value((uint32_t)mid, scale, gamma) >= (uint16_t)v) hi = mid; else lo = mid + 1;
+      }
+      thr[v] = (uint32_t)std::min<uint64_t>(lo, 0xffffffffull);
+    }
+    thr[0] = 0;
+    CU(c, cudaMemcpyAsync(c->d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,
+                          c->stream));
+  }
+  if (!c->d_gray) CU(c, cudaMalloc(&c->d_gray, sizeof(uint16_t) * c->cells));
+
+  // pass 2: the map itself, 4 B read + 2 B written per pixel
+  tonemap_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hist, c->d_gray, c->cells, c->d_lut, lut_size,
+                                                c->d_thr, big_endian ? 1 : 0);
+  CU(c, cudaGetLastError());
+  c->launches += 1;
+  CU(c, cudaEventRecord(c->ev_tb, c->stream));
+  c->tonemap_timed = true;
+  CU(c, cudaMemcpyAsync(host_out, c->d_gray, sizeof(uint16_t) * c->cells, cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_last_tonemap_ms(buddha_ctx *c, float *ms) {
+  if (!c || !ms) return BUDDHA_EINVAL;
+  if (!c->tonemap_timed) return fail(c, BUDDHA_EINVAL, "no tone-map call has been timed yet");
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaEventSynchronize(c->ev_tb));
+  CU(c, cudaEventElapsedTime(ms, c->ev_ta, c->ev_tb));
+  return BUDDHA_OK;
+}
+
+void *buddha_device_histogram(buddha_ctx *c) { return c ? (void *)c->d_hist : nullptr; }
+void *buddha_stream(buddha_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int buddha_merge(buddha_ctx **ctxs, int n, int root) {
+  if (!ctxs || n < 1 || root < 0 || root >= n) return BUDDHA_EINVAL;
+  if (n == 1) return BUDDHA_OK;
+  buddha_ctx *r = ctxs[root];
+  for (int i = 0; i < n; i++) {
+    if (!ctxs[i]) return BUDDHA_EINVAL;
+    if (ctxs[i]->cells != r->cells) return fail(r, BUDDHA_ESIZE, "contexts differ in canvas size");
+  }
+  NcclApi *nccl = load_nccl();
+  if (!nccl) return fail(r, BUDDHA_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  std::vector<int> devs(n);
+  std::vector<void *> comms(n, nullptr);
+  for (int i = 0; i < n; i++) devs[i] = ctxs[i]->params.device;
+  int rc = nccl->CommInitAll(comms.data(), n, devs.data());
+  if (rc) return fail(r, BUDDHA_ENCCL, "ncclCommInitAll: %s",
+                      nccl->GetErrorString ? nccl->GetErrorString(rc) : "error");
+  rc = nccl->GroupStart();
+  for (int i = 0; i < n && !rc; i++) {
+    cudaSetDevice(devs[i]);
+    rc = nccl->Reduce(ctxs[i]->d_hist, ctxs[i]->d_hist, r->cells, /*ncclUint32*/ 3, /*ncclSum*/ 0,
+                      root, comms[i], ctxs[i]->stream);
+  }
+  int rc2 = nccl->GroupEnd();
+  if (!rc) rc = rc2;
+  for (int i = 0; i < n; i++) {
+    cudaSetDevice(devs[i]);
+    cudaStreamSynchronize(ctxs[i]->stream);
+  }
+  for (int i = 0; i < n; i++) nccl->CommDestroy(comms[i]);
+  if (rc) return fail(r, BUDDHA_ENCCL, "ncclReduce: %s",
+                      nccl->GetErrorString ? nccl->GetErrorString(rc) : "error");
+  return BUDDHA_OK;
+}
+
+int buddha_probe_fp64_peak(buddha_ctx *c, double *lane_instr_per_s) {
+  if (!c || !lane_instr_per_s) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  double *d_out = nullptr;
+  CU(c, cudaMalloc(&d_out, sizeof(double)));
+  const int blocks = c->sm_count * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(c, cudaEventRecord(c->ev_ta, c->stream));
+    probe_dfma_kernel<<<blocks, 256, 0, c->stream>>>(d_out, iters, 1.0000001, 1e-9);
+    CU(c, cudaEventRecord(c->ev_tb, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev_ta, c->ev_tb));
+    double rate = (double)blocks * 256.0 * iters * 64.0 / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  cudaFree(d_out);
+  c->tonemap_timed = false;
+  *lane_instr_per_s = best;
+  return BUDDHA_OK;
+}
+
+int buddha_probe_red_peak(buddha_ctx *c, size_t footprint_bytes, double *red_per_s) {
+  if (!c || !red_per_s || footprint_bytes < 4) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  uint32_t *buf = nullptr;
+  unsigned long long cells = footprint_bytes / 4;
+  CU(c, cudaMalloc(&buf, cells * 4));
+  CU(c, cudaMemsetAsync(buf, 0, cells * 4, c->stream));
+  const int blocks = c->sm_count * 8, per_thread = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(c, cudaEventRecord(c->ev_ta, c->stream));
+    probe_red_kernel<<<blocks, 256, 0, c->stream>>>(buf, cells, per_thread, (uint32_t)rep);
+    CU(c, cudaEventRecord(c->ev_tb, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev_ta, c->ev_tb));
+    double rate = (double)blocks * 256.0 * per_thread / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  cudaFree(buf);
+  c->tonemap_timed = false;
+  *red_per_s = best;
+  return BUDDHA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,619 @@
+// buddha_kernels.cuh -- sm_100a device code of libbuddha: the Buddhabrot hot path.
+//
+// Replaces the reference's two kernels (InitializeRNG cudabrot.cu:146-149, DrawBuddhabrot
+// :379-414 with :284-365) and moves its serial host tone-map (:416-468) to the GPU.
+// Results are bit-identical to the reference's arithmetic: every FP64 operation
+// is pinned with a round-to-nearest intrinsic so neither NVVM nor ptxas can re-associate or
+// re-contract it.  DESIGN.md derives the identities used below.
+//
+// Orbit state is kept SCALED BY TWO: X = 2*re, Y = 2*im, CX = 2*c_re, CY = 2*c_im.  Scaling by a
+// power of two is exact (no value on this path can overflow or go subnormal),
+// so each rounding below is the reference's rounding of the same quantity times a power of two:
+//     A4 = rn(Y*Y)            = 4*rn(im*im)                 DMUL
+//     B4 = fma(X, X, -A4)     = 4*fma(re, re, -rn(im*im))   DFMA
+//     X' = fma(B4, 0.5, CX)   = 2*rn(c_re + B)              DFMA  (replaces DADD re+re AND DADD c+t2)
+//     Y' = fma(X, Y, CY)      = 2*fma(rn(re+re), im, c_im)  DFMA
+//     S4 = fma(Y',Y', rn(X'*X')) = 4*fma(im',im', rn(re'*re'));  escaped <=> S4 > 16
+// i.e. 4 FP64 instructions per step instead of the reference's 5, with identical bits.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace buddha {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kGenPerLane = 4;                 // candidates drawn per lane per generation batch
+constexpr int kCandCap = 32 + 32 * kGenPerLane; // fresh-candidate stack (per warp)
+constexpr int kDeepCap = 96;                   // long-running escape tests (per warp)
+constexpr int kOrbCap = 64;                    // accepted samples waiting for the orbit pass
+constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
+constexpr int kShortIters = 32;                // escape tests longer than this go to the deep list
+constexpr int kBlock = 8;                      // unchecked steps per deep block
+constexpr int kDeepExit = 24;                  // leave a phase when fewer lanes than this are busy
+constexpr int kOrbExit = 16;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Fast binning: T = fma(X, inv_half, C0) lands in [1.5*2^40, 1.5*2^40 + 2^20) for in-range
+// quotients, where the low mantissa word holds quotient * 2^12.
+constexpr int kBinFracBits = 12;
+constexpr uint32_t kBinHiWord = 0x42780000u;   // high word of 1.5 * 2^40
+
+enum CounterSlot {
+  kCntRejected = 0, kCntHitMax, kCntTooEarly, kCntAccepted, kCntEscapeIters, kCntOrbitPoints,
+  kCntIncrements, kCntExecuted, kCntShortcut, kCntExactBins, kCntSlots
+};
+
+struct RenderParams {
+  // canvas in the reference's form (exact binning path), cudabrot.cu:46-58
+  int32_t w, h;
+  double min_re, min_im, delta_re, delta_im;
+  // fast binning constants (host-computed, see buddha_api.cu: make_fast_bin)
+  double inv_half_re, inv_half_im;
+  double c0_lo_re, c0_hi_re, c0_lo_im, c0_hi_im;
+  int32_t fast_bin;
+  int32_t max_it, min_it;
+  int32_t shortcut;
+  uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
+  unsigned long long end;       // one past the last sample index of this launch
+};
+
+// ---- small helpers --------------------------------------------------------------------------
+
+__device__ __forceinline__ void red_add_u32(uint32_t *addr) {
+  asm volatile("red.global.add.u32 [%0], 1;" ::"l"(addr) : "memory");
+}
+
+__device__ __forceinline__ unsigned lane_id() {
+  unsigned l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// One step of z <- z^2 + c on the scaled state (4 FP64 instructions).
+#define BUDDHA_ZSTEP(x, y, cx, cy)              \
+  do {                                          \
+    double a4_ = __dmul_rn((y), (y));           \
+    double b4_ = __fma_rn((x), (x), -a4_);      \
+    double yn_ = __fma_rn((x), (y), (cy));      \
+    (x) = __fma_rn(b4_, 0.5, (cx));             \
+    (y) = yn_;                                  \
+  } while (0)
+
+// 4 * (re^2 + im^2) with the reference's rounding order (cudabrot.cu:336).
+__device__ __forceinline__ double norm4(double x, double y) {
+  return __fma_rn(y, y, __dmul_rn(x, x));
+}
+
+// Philox4x32-10 (curand_philox4x32_x.h:88-91,159-192), counter = (s_lo, s_hi, 0, 0).
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long s, const RenderParams &p) {
+  uint32_t c0 = (uint32_t)s, c1 = (uint32_t)(s >> 32), c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ p.key0[r];
+    uint32_t n2 = hi0 ^ c3 ^ p.key1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// _curand_uniform_double_hq (curand_uniform.h:101-105) followed by cudabrot.cu:392-393, scaled by
+// two: returns 2*(u*4-2) = fma(u, 8, -4).  The 53-bit integer is converted with two exact DADDs
+// (magic-number trick) instead of I2F.F64.U64.
+__device__ __forceinline__ double coord2_from_words(uint32_t x, uint32_t y) {
+  uint32_t lo = x ^ (y << 21);
+  uint32_t hi = y >> 11;
+  double dhi = __hiloint2double(0x45300000, (int)hi);  // 2^84 + hi * 2^32
+  double dlo = __hiloint2double(0x43300000, (int)lo);  // 2^52 + lo
+  double z = __dadd_rn(__dadd_rn(dhi, -(0x1p84 + 0x1p52)), dlo);  // exact: z < 2^53
+  double u = __fma_rn(z, 0x1p-53, 0x1p-54);
+  return __fma_rn(u, 8.0, -4.0);
+}
+
+// InMainCardioid || InOrder2Bulb (cudabrot.cu:284-298) on the scaled candidate:
+// 4*i2, 2*q0, 4*q, 16*lhs vs 16*rn(i2*0.25) = 4*i2, and 4*b vs 4/16.
+__device__ __forceinline__ bool rejected2(double cx, double cy) {
+  double i2 = __dmul_rn(cy, cy);            // 4 * rn(im*im)
+  double q0 = __dadd_rn(cx, -0.5);          // 2 * (re - 0.25)
+  double q = __fma_rn(q0, q0, i2);          // 4 * q
+  double s = __fma_rn(q0, 2.0, q);          // 4 * rn(q0 + q)
+  double lhs = __dmul_rn(q, s);             // 16 * rn(q * (q0 + q))
+  double t = __dadd_rn(cx, 2.0);            // 2 * (re + 1)
+  double b = __fma_rn(t, t, i2);            // 4 * fma(t, t, i2)
+  return (lhs < i2) || (b < 0.25);
+}
+
+// ---- binning --------------------------------------------------------------------------------
+
+// IncrementPixelCounter (cudabrot.cu:302-314) verbatim in arithmetic: IEEE subtract, IEEE divide,
+// cvt.rzi (saturating), 32-bit index.
+__device__ __forceinline__ bool bin_exact(double x2, double y2, const RenderParams &p,
+                                          uint32_t *hist) {
+  double re = __dmul_rn(x2, 0.5), im = __dmul_rn(y2, 0.5);
+  if ((re < p.min_re) || (im < p.min_im)) return false;
+  int col = __double2int_rz(__ddiv_rn(__dsub_rn(re, p.min_re), p.delta_re));
+  int row = __double2int_rz(__ddiv_rn(__dsub_rn(im, p.min_im), p.delta_im));
+  if ((row >= 0) && (row < p.h) && (col >= 0) && (col < p.w)) {
+    red_add_u32(hist + ((row * p.w) + col));
+    return true;
+  }
+  return false;
+}
+
+// Division-free binning.  For each axis two roundings of (quotient +- 2^-11) onto a 2^-12 grid are
+// produced by one DFMA each; if both floors agree, that floor is the reference's truncated IEEE
+// quotient, otherwise the point takes bin_exact.  Returns true if a cell
+// was incremented; *exact is set when the slow path was needed.
+__device__ __forceinline__ bool bin_point(double x2, double y2, const RenderParams &p,
+                                          uint32_t *hist, bool *exact) {
+  double tch = __fma_rn(x2, p.inv_half_re, p.c0_hi_re);
+  double tcl = __fma_rn(x2, p.inv_half_re, p.c0_lo_re);
+  double trh = __fma_rn(y2, p.inv_half_im, p.c0_hi_im);
+  double trl = __fma_rn(y2, p.inv_half_im, p.c0_lo_im);
+  // in-range <=> high words equal that of 1.5*2^40 (quotient + eps in [0, 2^20))
+  if (((uint32_t)__double2hiint(tch) != kBinHiWord) | ((uint32_t)__double2hiint(trh) != kBinHiWord))
+    return false;
+  uint32_t ch = (uint32_t)__double2loint(tch), cl = (uint32_t)__double2loint(tcl);
+  uint32_t rh = (uint32_t)__double2loint(trh), rl = (uint32_t)__double2loint(trl);
+  // the low-side values must sit in the same binade (else quotient - eps < 0: boundary hazard)
+  bool same = (((ch ^ cl) | (rh ^ rl)) >> kBinFracBits) == 0u &&
+              (uint32_t)__double2hiint(tcl) == kBinHiWord &&
+              (uint32_t)__double2hiint(trl) == kBinHiWord;
+  if (!same) {
+    *exact = true;
+    return bin_exact(x2, y2, p, hist);
+  }
+  uint32_t col = ch >> kBinFracBits, row = rh >> kBinFracBits;
+  if (col < (uint32_t)p.w && row < (uint32_t)p.h) {
+    red_add_u32(hist + (row * (uint32_t)p.w + col));
+    return true;
+  }
+  return false;
+}
+
+// ---- the simple kernel (debug / cross-check): one sample per thread, reference dataflow ------
+
+__global__ void __launch_bounds__(256)
+render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restrict__ hist,
+                     unsigned long long *__restrict__ counters) {
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long n_rej = 0, n_hit = 0, n_early = 0, n_acc = 0, e_ref = 0, pts = 0, inc = 0;
+  for (unsigned long long s = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       s < p.end; s += stride) {
+    uint4 r = philox4x32_10(s, p);
+    double cre = __dmul_rn(coord2_from_words(r.x, r.y), 0.5);
+    double cim = __dmul_rn(coord2_from_words(r.z, r.w), 0.5);
+    // cudabrot.cu:284-298, SASS dataflow of SURVEY.md 8(c)
+    double i2 = __dmul_rn(cim, cim);
+    double q0 = __dadd_rn(cre, -0.25);
+    double q = __fma_rn(q0, q0, i2);
+    bool card = __dmul_rn(q, __dadd_rn(q0, q)) < __dmul_rn(i2, 0.25);
+    double t = __dadd_rn(cre, 1.0);
+    bool bulb = __fma_rn(t, t, i2) < 0.0625;
+    if (card || bulb) { n_rej++; continue; }
+    // cudabrot.cu:319-340
+    double re = cre, im = cim;
+    int i = p.max_it;
+    for (int k = 0; k < p.max_it; k++) {
+      double t1 = __dmul_rn(im, im);
+      double t2 = __fma_rn(re, re, -t1);
+      double r2 = __dadd_rn(re, re);
+      im = __fma_rn(r2, im, cim);
+      re = __dadd_rn(cre, t2);
+      if (__fma_rn(im, im, __dmul_rn(re, re)) > 4.0) { i = k; break; }
+    }
+    if (i >= p.max_it) { n_hit++; e_ref += (p.max_it > 0 ? p.max_it : 0); continue; }
+    e_ref += i + 1;
+    if (i < p.min_it) { n_early++; continue; }
+    n_acc++;
+    // cudabrot.cu:347-365
+    re = cre; im = cim;
+    for (;;) {
+      double t1 = __dmul_rn(im, im);
+      double t2 = __fma_rn(re, re, -t1);
+      double r2 = __dadd_rn(re, re);
+      im = __fma_rn(r2, im, cim);
+      re = __dadd_rn(cre, t2);
+      pts++;
+      if (bin_exact(__dmul_rn(re, 2.0), __dmul_rn(im, 2.0), p, hist)) inc++;
+      if (__fma_rn(im, im, __dmul_rn(re, re)) > 4.0) break;
+    }
+  }
+  unsigned long long v[kCntSlots] = {n_rej, n_hit, n_early, n_acc, e_ref, pts, inc, e_ref, 0, pts};
+#pragma unroll
+  for (int k = 0; k < kCntSlots; k++) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    if (lane_id() == 0 && x) atomicAdd(counters + k, x);
+  }
+}
+
+// ---- the persistent renderer ----------------------------------------------------------------
+
+struct WarpQueues {
+  double cand_cx[kCandCap], cand_cy[kCandCap];
+  double deep_cx[kDeepCap], deep_cy[kDeepCap], deep_x[kDeepCap], deep_y[kDeepCap];
+  double orb_cx[kOrbCap], orb_cy[kOrbCap], orb_x[kOrbCap], orb_y[kOrbCap];
+  int deep_it[kDeepCap];
+  int orb_n[kOrbCap];
+};
+
+// Per-warp state that lives in registers for the whole kernel.
+struct WarpState {
+  int cand_n, deep_n, orb_n;               // stack heights (warp-uniform)
+  unsigned long long chunk_next, chunk_end; // sample indices still owned by this warp
+  bool exhausted;                          // the global cursor ran past p.end
+  // per-lane event counters, flushed to global memory at every cursor grab
+  uint32_t n_rej, n_hit, n_early, n_acc, n_cyc, n_exact;
+  uint32_t e_ref, e_exec, p_pts, p_inc;
+};
+
+__device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
+  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, ws.n_early, ws.n_acc, ws.e_ref, ws.p_pts,
+                           ws.p_inc, ws.e_exec, ws.n_cyc, ws.n_exact};
+#pragma unroll
+  for (int k = 0; k < kCntSlots; k++) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    if (lane_id() == 0 && x) atomicAdd(counters + k, x);
+  }
+  ws.n_rej = ws.n_hit = ws.n_early = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
+  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+}
+
+// Push one entry per lane with `pred` set onto a stack; returns the slot (valid where pred).
+__device__ __forceinline__ int stack_push(bool pred, int &height) {
+  unsigned m = __ballot_sync(kFull, pred);
+  int slot = height + __popc(m & lanemask_lt());
+  height += __popc(m);
+  return slot;
+}
+
+// Pop one entry for every lane with `want` set while entries last; returns the slot or -1.
+__device__ __forceinline__ int stack_pop(bool want, int &height) {
+  unsigned m = __ballot_sync(kFull, want);
+  int rank = __popc(m & lanemask_lt());
+  int slot = (want && rank < height) ? (height - 1 - rank) : -1;
+  int taken = min(__popc(m), height);
+  height -= taken;
+  return slot;
+}
+
+// (a) sampler: draw kGenPerLane candidates per lane from the Philox stream, reject the main
+// cardioid / period-2 bulb at full lane utilisation, and stack the survivors.
+__device__ __forceinline__ void generate(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                         unsigned long long *cursor,
+                                         unsigned long long *counters) {
+  const unsigned lane = lane_id();
+#pragma unroll 1
+  for (int g = 0; g < kGenPerLane; g++) {
+    if (ws.chunk_next >= ws.chunk_end) {
+      if (ws.exhausted) break;
+      flush_counters(ws, counters);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+      base = __shfl_sync(kFull, base, 0);
+      if (base >= p.end) { ws.exhausted = true; break; }
+      ws.chunk_next = base;
+      ws.chunk_end = (base + kChunk < p.end) ? base + kChunk : p.end;
+    }
+    unsigned long long s = ws.chunk_next + lane;
+    bool valid = s < ws.chunk_end;
+    ws.chunk_next = (ws.chunk_next + 32 < ws.chunk_end) ? ws.chunk_next + 32 : ws.chunk_end;
+    uint4 r = philox4x32_10(s, p);
+    double cx = coord2_from_words(r.x, r.y);
+    double cy = coord2_from_words(r.z, r.w);
+    bool rej = rejected2(cx, cy);
+    bool keep = valid && !rej;
+    ws.n_rej += (valid && rej) ? 1u : 0u;
+    if (p.max_it <= 0) {  // IterateMandelbrot returns max at once (cudabrot.cu:326,339,407)
+      ws.n_hit += keep ? 1u : 0u;
+      keep = false;
+    }
+    int slot = stack_push(keep, ws.cand_n);
+    if (keep) { q.cand_cx[slot] = cx; q.cand_cy[slot] = cy; }
+  }
+  __syncwarp();
+}
+
+// (b) escape test with per-lane refill: every lane owns one candidate; a lane whose candidate
+// escaped (or reached the short limit) is refilled from the candidate stack in the same round.
+// Returns when a downstream list needs service or when the sample range is exhausted and every
+// lane is idle.
+__device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                            unsigned long long *cursor,
+                                            unsigned long long *counters) {
+  const int lim = min(p.max_it, kShortIters);
+  bool act = false;
+  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
+  int it = 0;
+#pragma unroll 1
+  for (;;) {
+    unsigned need = __ballot_sync(kFull, !act);
+    if (need) {
+      if (ws.cand_n < __popc(need) && !(ws.exhausted && ws.chunk_next >= ws.chunk_end))
+        generate(p, q, ws, cursor, counters);
+      int slot = stack_pop(!act, ws.cand_n);
+      if (slot >= 0) {
+        cx = q.cand_cx[slot]; cy = q.cand_cy[slot];
+        x = cx; y = cy; it = 0; act = true;
+      }
+      __syncwarp();
+      if (__ballot_sync(kFull, act) == 0u) return;  // nothing left anywhere
+    }
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    it++;
+    bool esc = norm4(x, y) > 16.0;
+    bool fin = act && (esc || it >= lim);
+    if (__ballot_sync(kFull, fin)) {
+      bool hit = fin && !esc && (it >= p.max_it);
+      bool todeep = fin && !esc && !hit;
+      bool acc = fin && esc && (it - 1 >= p.min_it);
+      ws.n_acc += acc ? 1u : 0u;
+      ws.n_early += (fin && esc && !acc) ? 1u : 0u;
+      ws.n_hit += hit ? 1u : 0u;
+      ws.e_ref += (fin && !todeep) ? (uint32_t)it : 0u;   // esc: i+1 = it; hit: max = it
+      ws.e_exec += (fin && !todeep) ? (uint32_t)it : 0u;
+      ws.p_pts += acc ? (uint32_t)it : 0u;
+      int so = stack_push(acc, ws.orb_n);
+      if (acc) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = cx; q.orb_y[so] = cy; q.orb_n[so] = it; }
+      int sd = stack_push(todeep, ws.deep_n);
+      if (todeep) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
+      if (fin) { act = false; cx = cy = x = y = 0.0; }
+      if (ws.orb_n >= 32 || ws.deep_n >= 32) break;
+    }
+  }
+  // suspend: the candidates still in flight continue in the deep list from their current state
+  int sd = stack_push(act, ws.deep_n);
+  if (act) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
+  __syncwarp();
+}
+
+// (c) long escape tests, re-queued through the shared-memory list so that all 32 lanes iterate.
+// Each round runs kBlock unchecked steps (4 FP64 instr each) and tests |z|^2 once.  Because
+// |c| <= 2 here, an orbit that leaves the radius-2 disc cannot re-enter it,
+// so "escaped somewhere in the block" <=> "escaped at the end of the block"; the block is then
+// replayed from its saved start with the per-step test to get the exact iteration index.
+// A state that repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (shortcut).
+__device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                           bool drain) {
+  bool act = false, slow = false;
+  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
+  int it = 0;
+#pragma unroll 1
+  for (;;) {
+    if (ws.orb_n >= 32) break;  // keep room for 32 pushes
+    unsigned need = __ballot_sync(kFull, !act);
+    if (need && ws.deep_n > 0) {
+      int slot = stack_pop(!act, ws.deep_n);
+      if (slot >= 0) {
+        cx = q.deep_cx[slot]; cy = q.deep_cy[slot];
+        x = q.deep_x[slot]; y = q.deep_y[slot]; it = q.deep_it[slot];
+        rx = x; ry = y;
+        slow = !(norm4(cx, cy) <= 15.99);  // |c| too close to 2: always use the per-step test
+        act = true;
+      }
+      __syncwarp();
+    }
+    unsigned am = __ballot_sync(kFull, act);
+    if (am == 0u) break;
+    if (!drain && __popc(am) < kDeepExit) break;
+
+    const double x0 = x, y0 = y;
+    const int rem = p.max_it - it;
+    const bool fastok = act && !slow && rem >= kBlock;
+#pragma unroll
+    for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
+    const bool esc8 = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
+    bool replay = act && (!fastok || esc8);
+    bool esc = false, cyc = false;
+    if (fastok && !esc8) {
+      it += kBlock;
+      if (p.shortcut) {
+        if (__double_as_longlong(x) == __double_as_longlong(rx) &&
+            __double_as_longlong(y) == __double_as_longlong(ry)) {
+          cyc = true;
+        } else if ((it & (it - 1)) == 0) {
+          rx = x; ry = y;
+        }
+      }
+    }
+    if (__ballot_sync(kFull, replay)) {
+      if (replay) {
+        x = x0; y = y0;
+        const int n = min(kBlock, rem);
+#pragma unroll 1
+        for (int k = 0; k < n; k++) {
+          BUDDHA_ZSTEP(x, y, cx, cy);
+          it++;
+          if (norm4(x, y) > 16.0) { esc = true; break; }
+        }
+        ws.e_exec += fastok ? (uint32_t)kBlock : 0u;  // the unchecked pass that was discarded
+      }
+    }
+    bool hit = act && !esc && (cyc || it >= p.max_it);
+    bool fin = act && (esc || hit);
+    if (__ballot_sync(kFull, fin)) {
+      bool acc = esc && (it - 1 >= p.min_it);
+      ws.n_acc += acc ? 1u : 0u;
+      ws.n_early += (esc && !acc) ? 1u : 0u;
+      ws.n_hit += hit ? 1u : 0u;
+      ws.n_cyc += (hit && it < p.max_it) ? 1u : 0u;
+      ws.e_ref += esc ? (uint32_t)it : (hit ? (uint32_t)p.max_it : 0u);
+      ws.e_exec += fin ? (uint32_t)it : 0u;
+      ws.p_pts += acc ? (uint32_t)it : 0u;
+      int so = stack_push(acc, ws.orb_n);
+      if (acc) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = cx; q.orb_y[so] = cy; q.orb_n[so] = it; }
+      if (fin) { act = false; cx = cy = x = y = 0.0; it = 0; }
+    }
+  }
+  int sd = stack_push(act, ws.deep_n);
+  if (act) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
+  __syncwarp();
+}
+
+// (d) orbit pass: re-iterate accepted samples for exactly i+1 steps (no escape test needed: the
+// count is known), scatter every point with a fire-and-forget red.global.add.u32.
+__device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                            uint32_t *hist, bool drain) {
+  bool act = false;
+  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
+  int n = 0;
+#pragma unroll 1
+  for (;;) {
+    unsigned need = __ballot_sync(kFull, !act);
+    if (need && ws.orb_n > 0) {
+      int slot = stack_pop(!act, ws.orb_n);
+      if (slot >= 0) {
+        cx = q.orb_cx[slot]; cy = q.orb_cy[slot];
+        x = q.orb_x[slot]; y = q.orb_y[slot]; n = q.orb_n[slot];
+        act = true;
+      }
+      __syncwarp();
+    }
+    unsigned am = __ballot_sync(kFull, act);
+    if (am == 0u) break;
+    if (!drain && __popc(am) < kOrbExit) break;
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    if (act) {
+      bool exact = false;
+      bool in = p.fast_bin ? bin_point(x, y, p, hist, &exact) : (exact = true, bin_exact(x, y, p, hist));
+      ws.p_inc += in ? 1u : 0u;
+      ws.n_exact += exact ? 1u : 0u;
+      if (--n == 0) { act = false; cx = cy = x = y = 0.0; }
+    }
+  }
+  int so = stack_push(act, ws.orb_n);
+  if (act) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = x; q.orb_y[so] = y; q.orb_n[so] = n; }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreadsPerCta)
+render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
+                         unsigned long long *__restrict__ cursor,
+                         unsigned long long *__restrict__ counters) {
+  __shared__ WarpQueues queues[kWarpsPerCta];
+  WarpQueues &q = queues[threadIdx.x >> 5];
+  WarpState ws;
+  ws.cand_n = ws.deep_n = ws.orb_n = 0;
+  ws.chunk_next = ws.chunk_end = 0;
+  ws.exhausted = false;
+  ws.n_rej = ws.n_hit = ws.n_early = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
+  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+
+#pragma unroll 1
+  for (;;) {
+    if (ws.orb_n >= 32) { orbit_phase(p, q, ws, hist, false); continue; }
+    if (ws.deep_n >= 32) { deep_phase(p, q, ws, false); continue; }
+    bool more = !(ws.exhausted && ws.chunk_next >= ws.chunk_end) || ws.cand_n > 0;
+    if (more) { short_phase(p, q, ws, cursor, counters); continue; }
+    if (ws.deep_n > 0) { deep_phase(p, q, ws, true); continue; }
+    if (ws.orb_n > 0) { orbit_phase(p, q, ws, hist, true); continue; }
+    break;
+  }
+  flush_counters(ws, counters);
+}
+
+// ---- tone-map (cudabrot.cu:416-468) ----------------------------------------------------------
+
+// GetLinearColorScale's max search (:430-435).
+__global__ void __launch_bounds__(256)
+hist_max_kernel(const uint32_t *__restrict__ hist, size_t cells, uint32_t *__restrict__ out_max) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t m = 0;
+  size_t vec = cells / 4;
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
+  for (size_t k = i; k < vec; k += stride) {
+    uint4 v = __ldg(h4 + k);
+    m = max(m, max(max(v.x, v.y), max(v.z, v.w)));
+  }
+  for (size_t k = vec * 4 + i; k < cells; k += stride) m = max(m, hist[k]);
+  m = __reduce_max_sync(kFull, m);
+  if (lane_id() == 0 && m) atomicMax(out_max, m);
+}
+
+// DoGammaCorrection per pixel (:443-449, :460-466) as a table lookup: lut[c] for c < lut_size is
+// the reference's 16-bit value for count c (already byte-swapped when the caller wants big-endian
+// output); counts beyond the table are resolved by a search in thr[v] = smallest count whose value
+// is >= v (the map is monotone in the count).
+__device__ __forceinline__ uint16_t tone_lookup(uint32_t c, const uint16_t *__restrict__ lut,
+                                                uint32_t lut_size,
+                                                const uint32_t *__restrict__ thr, int swap) {
+  if (c < lut_size) return __ldg(lut + c);
+  uint32_t lo = 0, hi = 65535;  // largest v with thr[v] <= c
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(thr + mid) <= c) lo = mid; else hi = mid - 1;
+  }
+  uint16_t v = (uint16_t)lo;
+  return swap ? (uint16_t)((v << 8) | (v >> 8)) : v;
+}
+
+__global__ void __launch_bounds__(256)
+tonemap_kernel(const uint32_t *__restrict__ hist, uint16_t *__restrict__ out, size_t cells,
+               const uint16_t *__restrict__ lut, uint32_t lut_size,
+               const uint32_t *__restrict__ thr, int swap) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t vec = cells / 4;
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
+  uint2 *o4 = reinterpret_cast<uint2 *>(out);
+  for (size_t k = i; k < vec; k += stride) {
+    uint4 v = __ldg(h4 + k);
+    uint32_t a = tone_lookup(v.x, lut, lut_size, thr, swap);
+    uint32_t b = tone_lookup(v.y, lut, lut_size, thr, swap);
+    uint32_t c = tone_lookup(v.z, lut, lut_size, thr, swap);
+    uint32_t d = tone_lookup(v.w, lut, lut_size, thr, swap);
+    o4[k] = make_uint2(a | (b << 16), c | (d << 16));
+  }
+  for (size_t k = vec * 4 + i; k < cells; k += stride)
+    out[k] = tone_lookup(hist[k], lut, lut_size, thr, swap);
+}
+
+// ---- roofline probes --------------------------------------------------------------------------
+
+// Peak FP64-pipe issue rate: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256)
+probe_dfma_kernel(double *out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5,
+         v6 = v0 + 6, v7 = v0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      v0 = __fma_rn(v0, a, b); v1 = __fma_rn(v1, a, b); v2 = __fma_rn(v2, a, b);
+      v3 = __fma_rn(v3, a, b); v4 = __fma_rn(v4, a, b); v5 = __fma_rn(v5, a, b);
+      v6 = __fma_rn(v6, a, b); v7 = __fma_rn(v7, a, b);
+    }
+  }
+  double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+  if (s == 12345.678) out[0] = s;  // keeps the chains alive
+}
+
+// red.global.add.u32 to uniformly random cells of a `cells`-entry array.
+__global__ void __launch_bounds__(256)
+probe_red_kernel(uint32_t *buf, unsigned long long cells, int per_thread, uint32_t salt) {
+  unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long s = (g + 1) * 0x9E3779B97F4A7C15ull + salt;
+#pragma unroll 4
+  for (int i = 0; i < per_thread; i++) {
+    s ^= s >> 30; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 27; s *= 0x94D049BB133111EBull; s ^= s >> 31;
+    unsigned long long idx = __umul64hi(s, cells);  // uniform in [0, cells)
+    red_add_u32(buf + idx);
+    s += 0x9E3779B97F4A7C15ull;
+  }
+}
+
+}  // namespace buddha

@@ -1,0 +1,165 @@
+"""Renderer: a thin object over one libbuddha context (one GPU).
+
+Mirrors the reference program's flow (cudabrot.cu:762-791): SetupCUDA -> LoadInProgressBuffer ->
+RenderImage -> SaveInProgressBuffer -> SaveImage, with each stage a method that calls straight
+through the C ABI.  Host buffers are numpy arrays; nothing here computes anything.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Renderer:
+    def __init__(self, width=1000, height=1000, max_iterations=100, min_iterations=20,
+                 canvas=(-2.0, 2.0, -2.0, 2.0), seed=1337, device=0, flags=0):
+        """canvas = (min_real, max_real, min_imag, max_imag).  Defaults = the reference's defaults
+        (cudabrot.cu:763-772, :530-543)."""
+        self._lib = capi.lib()
+        p = capi.default_params()
+        p.device = device
+        p.width, p.height = width, height
+        p.min_real, p.max_real, p.min_imag, p.max_imag = canvas
+        p.max_iterations, p.min_iterations = max_iterations, min_iterations
+        p.seed, p.flags = seed, flags
+        self.params = p
+        self.width, self.height = width, height
+        self.cells = width * height
+        self._ctx = C.c_void_p()
+        rc = self._lib.buddha_create(C.byref(self._ctx), C.byref(p))
+        if rc:
+            msg = self._lib.buddha_last_error(None).decode()
+            self._ctx = None
+            raise capi.BuddhaError(rc, msg)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.buddha_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise capi.BuddhaError(rc, self._lib.buddha_last_error(self._ctx).decode())
+
+    # -- histogram (the -s buffer surface, cudabrot.cu:215-280) -------------------------------
+    def clear(self):
+        self._check(self._lib.buddha_clear_histogram(self._ctx))
+
+    def load_histogram(self, hist):
+        h = np.ascontiguousarray(hist, dtype=np.uint32)
+        self._check(self._lib.buddha_load_histogram(self._ctx, h.ctypes.data, h.size))
+
+    def read_histogram(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.uint32)
+        self._check(self._lib.buddha_read_histogram(self._ctx, out.ctypes.data, out.size))
+        return out
+
+    # -- render (cudabrot.cu:379-414, :483-492) -----------------------------------------------
+    def render_samples(self, first, count):
+        self._check(self._lib.buddha_render_samples(self._ctx, first, count))
+
+    def render_samples_async(self, first, count):
+        self._check(self._lib.buddha_render_samples_async(self._ctx, first, count))
+
+    def sync(self):
+        self._check(self._lib.buddha_sync(self._ctx))
+
+    def render_seconds(self, seconds, first=0):
+        done, passes = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.buddha_render_seconds(self._ctx, seconds, None, first,
+                                                    C.byref(done), C.byref(passes)))
+        return done.value, passes.value
+
+    def last_render_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.buddha_last_render_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        c = capi.Counters()
+        self._check(self._lib.buddha_get_counters(self._ctx, C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._check(self._lib.buddha_reset_counters(self._ctx))
+
+    # -- tone-map (cudabrot.cu:416-468, :566-570) ----------------------------------------------
+    def tonemap(self, gamma=1.0, big_endian=False, out=None, want_image=True):
+        """Returns (uint16 image or None, max, scale)."""
+        mx, sc = C.c_uint32(), C.c_double()
+        ptr, n = None, 0
+        if want_image:
+            if out is None:
+                out = np.empty((self.height, self.width), dtype=np.uint16)
+            ptr, n = out.ctypes.data, out.size
+        self._check(self._lib.buddha_tonemap_u16(self._ctx, gamma, int(big_endian), ptr, n,
+                                                 C.byref(mx), C.byref(sc)))
+        return (out if want_image else None), mx.value, sc.value
+
+    def last_tonemap_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.buddha_last_tonemap_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    # -- multi-GPU plumbing --------------------------------------------------------------------
+    @property
+    def device_histogram_ptr(self):
+        return self._lib.buddha_device_histogram(self._ctx)
+
+    @property
+    def stream_ptr(self):
+        return self._lib.buddha_stream(self._ctx)
+
+    def histogram_as_tensor(self):
+        """The device histogram as a torch int32 tensor aliasing libbuddha's memory (no copy), so
+        torch.distributed can reduce it in place.  torch is plumbing here, nothing more."""
+        import torch
+
+        class _Alias:
+            pass
+
+        a = _Alias()
+        a.__cuda_array_interface__ = {
+            "shape": (self.cells,), "typestr": "<i4", "data": (self.device_histogram_ptr, False),
+            "version": 2, "strides": None,
+        }
+        return torch.as_tensor(a, device="cuda:%d" % self.params.device)
+
+    # -- roofline probes -----------------------------------------------------------------------
+    def probe_fp64_peak(self):
+        v = C.c_double()
+        self._check(self._lib.buddha_probe_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    def probe_red_peak(self, footprint_bytes):
+        v = C.c_double()
+        self._check(self._lib.buddha_probe_red_peak(self._ctx, footprint_bytes, C.byref(v)))
+        return v.value
+
+
+def merge_in_process(renderers, root=0):
+    """buddha_merge: sum the histograms of several in-process contexts into renderers[root]."""
+    L = capi.lib()
+    arr = (C.c_void_p * len(renderers))(*[r._ctx for r in renderers])
+    rc = L.buddha_merge(arr, len(renderers), root)
+    if rc:
+        raise capi.BuddhaError(rc, L.buddha_last_error(renderers[root]._ctx).decode())
+
+
+def write_pgm(path, image_be, width, height):
+    """SaveImage (cudabrot.cu:548-577) for an image that is already big-endian."""
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n%d\n" % (width, height, 0xffff))
+        f.write(np.ascontiguousarray(image_be, dtype=np.uint16).tobytes())

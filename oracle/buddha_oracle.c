@@ -312,3 +312,116 @@ uint64_t oracle_fnv1a64(const uint32_t *data, size_t cells) {
   for (size_t i = 0; i < cells * 4; i++) { hsh ^= b[i]; hsh *= 0x100000001b3ull; }
   return hsh;
 }
+
+/* ---- restatements of the product's transformed arithmetic (see header) ------------------- */
+
+int oracle_escape_iterations_scaled(double c_real, double c_imag, int max_iterations) {
+  double cx = c_real * 2.0, cy = c_imag * 2.0, x = cx, y = cy;
+  for (int i = 0; i < max_iterations; i++) {
+    double a4 = y * y;
+    double b4 = FMA(x, x, -a4);
+    double yn = FMA(x, y, cy);
+    x = FMA(b4, 0.5, cx);
+    y = yn;
+    if (FMA(y, y, x * x) > 16.0) return i;
+  }
+  return max_iterations;
+}
+
+int oracle_rejected_scaled(double c_real, double c_imag) {
+  double cx = c_real * 2.0, cy = c_imag * 2.0;
+  double i2 = cy * cy;
+  double q0 = cx + -0.5;
+  double q = FMA(q0, q0, i2);
+  double s = FMA(q0, 2.0, q);
+  double lhs = q * s;
+  double t = cx + 2.0;
+  double b = FMA(t, t, i2);
+  return (lhs < i2) || (b < 0.25);
+}
+
+int oracle_bin_reference(const oracle_dims *d, double re, double im, int64_t *index) {
+  return bin_point(re, im, d, index);
+}
+
+typedef struct { double inv_half, c0_lo, c0_hi; int ok; } fast_axis;
+
+/* make_fast_bin of csrc/buddha_api.cu */
+static fast_axis make_fast_axis(double min_v, double delta, int n) {
+  fast_axis f = {0, 0, 0, 0};
+  double inv = 1.0 / delta;
+  if (!(inv > 0.0) || !isfinite(inv)) return f;
+  if (n > (1 << 19)) return f;
+  if (!(fabs(min_v) * inv < 0x1p36)) return f;
+  long double base = (long double)0x1.8p40 - (long double)min_v * (long double)inv;
+  f.c0_hi = (double)(base + (long double)0x1p-11);
+  f.c0_lo = (double)(base - (long double)0x1p-11);
+  f.inv_half = inv * 0.5;
+  f.ok = 1;
+  return f;
+}
+
+static inline uint32_t hi32(double v) { uint64_t b; memcpy(&b, &v, 8); return (uint32_t)(b >> 32); }
+static inline uint32_t lo32(double v) { uint64_t b; memcpy(&b, &v, 8); return (uint32_t)b; }
+
+int oracle_bin_fast(const oracle_dims *d, double re, double im, int64_t *index, int *took_exact) {
+  fast_axis fr = make_fast_axis(d->min_real, d->delta_real, d->w);
+  fast_axis fi = make_fast_axis(d->min_imag, d->delta_imag, d->h);
+  *took_exact = 0;
+  if (!fr.ok || !fi.ok) return -1;
+  double x2 = re * 2.0, y2 = im * 2.0;
+  double tch = FMA(x2, fr.inv_half, fr.c0_hi), tcl = FMA(x2, fr.inv_half, fr.c0_lo);
+  double trh = FMA(y2, fi.inv_half, fi.c0_hi), trl = FMA(y2, fi.inv_half, fi.c0_lo);
+  const uint32_t H0 = 0x42780000u;
+  if (hi32(tch) != H0 || hi32(trh) != H0) return 0;
+  uint32_t ch = lo32(tch), cl = lo32(tcl), rh = lo32(trh), rl = lo32(trl);
+  int same = ((((ch ^ cl) | (rh ^ rl)) >> 12) == 0u) && hi32(tcl) == H0 && hi32(trl) == H0;
+  if (!same) {
+    *took_exact = 1;
+    return bin_point(x2 * 0.5, y2 * 0.5, d, index);
+  }
+  uint32_t col = ch >> 12, row = rh >> 12;
+  if (col < (uint32_t)d->w && row < (uint32_t)d->h) {
+    *index = (int64_t)(row * (uint32_t)d->w + col);
+    return 1;
+  }
+  return 0;
+}
+
+uint64_t oracle_check_scaled(uint64_t seed, uint64_t first, uint64_t count, int max_iterations) {
+  uint64_t bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : bad)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    int r1 = oracle_rejected(cre, cim), r2 = oracle_rejected_scaled(cre, cim);
+    if (r1 != r2) { bad++; continue; }
+    if (r1) continue;
+    if (oracle_escape_iterations(cre, cim, max_iterations) !=
+        oracle_escape_iterations_scaled(cre, cim, max_iterations)) bad++;
+  }
+  return bad;
+}
+
+uint64_t oracle_check_fast_bin(const oracle_dims *d, const double *points, uint64_t n,
+                               uint64_t *exact_count, uint64_t *in_canvas) {
+  uint64_t bad = 0, ex = 0, in = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : bad, ex, in)
+#endif
+  for (uint64_t k = 0; k < n; k++) {
+    int64_t i1 = -1, i2 = -1;
+    int took = 0;
+    int a = oracle_bin_reference(d, points[2 * k], points[2 * k + 1], &i1);
+    int b = oracle_bin_fast(d, points[2 * k], points[2 * k + 1], &i2, &took);
+    if (b < 0) { bad++; continue; }
+    if (a != b || (a && i1 != i2)) bad++;
+    ex += (uint64_t)took;
+    in += (uint64_t)a;
+  }
+  if (exact_count) *exact_count = ex;
+  if (in_canvas) *in_canvas = in;
+  return bad;
+}

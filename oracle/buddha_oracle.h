@@ -88,6 +88,33 @@ uint64_t oracle_fnv1a64(const uint32_t *data, size_t cells);
 
 int oracle_max_threads(void);
 
+/* ---- CPU restatements of the PRODUCT's transformed arithmetic --------------------------------
+ * The kernels do not run the reference dataflow literally: they keep the orbit scaled by two
+ * (4 FP64 instructions per step) and bin without divisions.  These functions restate those two
+ * transformations on the CPU so tests can compare them with the reference-form functions above
+ * over millions of ordinary and adversarial inputs without a GPU. */
+
+/* Escape index computed with the scaled recurrence of csrc/buddha_kernels.cuh (BUDDHA_ZSTEP). */
+int oracle_escape_iterations_scaled(double c_real, double c_imag, int max_iterations);
+
+/* cardioid/bulb test on the scaled candidate (rejected2 in buddha_kernels.cuh). */
+int oracle_rejected_scaled(double c_real, double c_imag);
+
+/* Reference binning (cudabrot.cu:302-314): returns 1 and the cell index if (re, im) is counted. */
+int oracle_bin_reference(const oracle_dims *d, double re, double im, int64_t *index);
+
+/* Division-free binning of bin_point (two DFMA roundings per axis); *took_exact is set when the
+ * fast path declined and the IEEE-division path decided.  Returns -1 if the canvas does not
+ * admit the fast path at all (product falls back to exact binning for every point). */
+int oracle_bin_fast(const oracle_dims *d, double re, double im, int64_t *index, int *took_exact);
+
+/* Batch checkers for the two functions above (OpenMP).  Both return the number of mismatches
+ * against the reference-form functions (0 = identical everywhere). */
+uint64_t oracle_check_scaled(uint64_t seed, uint64_t first, uint64_t count, int max_iterations);
+/* points = n (re, im) pairs; *exact_count receives how many took the division path. */
+uint64_t oracle_check_fast_bin(const oracle_dims *d, const double *points, uint64_t n,
+                               uint64_t *exact_count, uint64_t *in_canvas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,16 @@ def lib():
         L.oracle_fnv1a64.argtypes = [u32p, C.c_size_t]
         L.oracle_fnv1a64.restype = C.c_uint64
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_escape_iterations_scaled.argtypes = [C.c_double, C.c_double, C.c_int]
+        L.oracle_escape_iterations_scaled.restype = C.c_int
+        L.oracle_check_scaled.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+        L.oracle_check_scaled.restype = C.c_uint64
+        L.oracle_check_fast_bin.argtypes = [C.POINTER(Dims), C.POINTER(C.c_double), C.c_uint64,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.oracle_check_fast_bin.restype = C.c_uint64
+        L.oracle_bin_fast.argtypes = [C.POINTER(Dims), C.c_double, C.c_double,
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.oracle_bin_fast.restype = C.c_int
         _lib = L
     return _lib
 
@@ -150,3 +160,26 @@ def fnv1a64(hist):
 
 def max_threads():
     return int(lib().oracle_max_threads())
+
+
+def check_scaled(seed, first, count, max_iter):
+    """Mismatches between the reference-form and the product's scaled recurrence / rejection."""
+    return int(lib().oracle_check_scaled(seed, first, count, max_iter))
+
+
+def check_fast_bin(dims, points):
+    """(mismatches, points that took the division path, points in canvas); mismatches is None
+    when the canvas does not admit the division-free path."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    idx, took = C.c_int64(), C.c_int()
+    if lib().oracle_bin_fast(C.byref(dims), 0.0, 0.0, C.byref(idx), C.byref(took)) < 0:
+        return None, 0, 0
+    ex, inc = C.c_uint64(), C.c_uint64()
+    bad = lib().oracle_check_fast_bin(C.byref(dims), _p(pts, C.c_double), len(pts), C.byref(ex),
+                                      C.byref(inc))
+    return int(bad), int(ex.value), int(inc.value)
+
+
+def run_ref_probe(*args):
+    """Run oracle/_ref/ref_probe (the reference's own code, prebuilt); returns CompletedProcess."""
+    return subprocess.run([REF_PROBE] + [str(a) for a in args], capture_output=True, text=True)

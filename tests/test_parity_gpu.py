@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FULL = (-2.0, 2.0, -2.0, 2.0)
+
+COUNTER_KEYS = ["candidates", "rejected", "hit_max", "too_early", "accepted", "escape_iters",
+                "orbit_points", "increments"]
+
+
+def gpu_render(buddha, w, h, m, c, seed, first, count, canvas=FULL, flags=0):
+    with buddha.Renderer(w, h, m, c, canvas=canvas, seed=seed, flags=flags) as r:
+        r.render_samples(first, count)
+        return r.read_histogram(), r.counters()
+
+
+def assert_same(hist, cnt, ohist, ocnt):
+    for k in COUNTER_KEYS:
+        assert cnt[k] == ocnt[k], (k, cnt[k], ocnt[k])
+    assert hist.dtype == np.uint32 and hist.shape == ohist.shape
+    assert np.array_equal(hist, ohist)
+
+
+# BASELINE.json configs at sizes the oracle finishes in seconds
+CASES = {
+    "cfg1_full_2^24": (1000, 1000, 100, 20, FULL, 1 << 24),
+    "cfg2_deep": (4000, 4000, 20000, 10000, FULL, 1 << 22),
+    "cfg3_small_canvas": (2000, 2000, 2000, 20, FULL, 1 << 22),
+    "cfg4_zoom": (8000, 4000, 5000, 20, (0.0, 1.0, 0.0, 0.5), 1 << 21),
+    "cfg5_ch1": (1000, 1000, 1000, 20, FULL, 1 << 21),
+    "ragged_count": (333, 77, 300, 5, (-1.7, 0.3, -0.123, 0.777), 100003),
+    "tiny": (3, 5, 64, 0, FULL, 4097),
+    "min_gt_max": (64, 64, 50, 60, FULL, 1 << 16),
+    "m_zero": (64, 64, 0, 0, FULL, 1 << 14),
+    "m_one": (64, 64, 1, 0, FULL, 1 << 16),
+    "m_33_block_tail": (128, 128, 37, 3, FULL, 1 << 18),
+    "extreme_zoom_exact_binning": (500, 500, 400, 10,
+                                   (-0.743644786, -0.7436447859, 0.1318252536, 0.1318252537),
+                                   1 << 20),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_histogram_and_counters_match_oracle(buddha, oracle, name):
+    w, h, m, c, canvas, n = CASES[name]
+    ohist, ocnt, _ = oracle.render(w, h, m, c, 1337, 0, n, canvas=canvas)
+    hist, cnt = gpu_render(buddha, w, h, m, c, 1337, 0, n, canvas)
+    assert_same(hist, cnt, ohist, ocnt)
+
+
+@pytest.mark.parametrize("flags_name", ["F_NO_SHORTCUT", "F_SIMPLE_KERNEL", "F_EXACT_BINNING"])
+def test_kernel_variants_agree(buddha, oracle, flags_name):
+    """The periodicity shortcut, the division-free binning and the persistent scheduling change
+    nothing in the output."""
+    flags = getattr(buddha, flags_name)
+    for (w, h, m, c, canvas, n) in [(512, 512, 3000, 100, FULL, 1 << 20),
+                                    (800, 400, 500, 20, (0.0, 1.0, 0.0, 0.5), 1 << 20)]:
+        ohist, ocnt, _ = oracle.render(w, h, m, c, 7, 123456789, n, canvas=canvas)
+        hist, cnt = gpu_render(buddha, w, h, m, c, 7, 123456789, n, canvas, flags=flags)
+        assert_same(hist, cnt, ohist, ocnt)
+
+
+def test_shortcut_statistics(buddha):
+    with buddha.Renderer(256, 256, 20000, 10000) as r:
+        r.render_samples(0, 1 << 22)
+        c = r.counters()
+    assert c["shortcut_hits"] > 0.5 * c["hit_max"]
+    assert c["executed_iters"] < c["escape_iters"]
+    with buddha.Renderer(256, 256, 20000, 10000, flags=buddha.F_NO_SHORTCUT) as r:
+        r.render_samples(0, 1 << 20)
+        c = r.counters()
+    assert c["shortcut_hits"] == 0 and c["executed_iters"] >= c["escape_iters"]
+
+
+def test_sample_ranges_are_additive_and_64bit(buddha, oracle):
+    """Any split of an index range over calls gives the same summed histogram; indices beyond
+    2^32 use the high counter word."""
+    first = (1 << 40) + 12345
+    n = 300000
+    ohist, ocnt, _ = oracle.render(200, 200, 150, 10, 99, first, n)
+    with buddha.Renderer(200, 200, 150, 10, seed=99) as r:
+        r.render_samples(first, 1000)
+        r.render_samples(first + 1000, 0)
+        r.render_samples(first + 1000, 4096 * 3 + 5)
+        r.render_samples_async(first + 1000 + 4096 * 3 + 5, n - (1000 + 4096 * 3 + 5))
+        r.sync()
+        assert r.last_render_ms() > 0
+        assert_same(r.read_histogram(), r.counters(), ohist, ocnt)
+        r.reset_counters()
+        assert r.counters()["candidates"] == 0
+
+
+def test_full_size_cfg3_histogram(buddha, oracle):
+    """20000x20000 (1.6 GB histogram, BASELINE config 3) at a reduced sample count."""
+    n = 1 << 21
+    ohist, ocnt, _ = oracle.render(20000, 20000, 2000, 20, 1337, 0, n)
+    hist, cnt = gpu_render(buddha, 20000, 20000, 2000, 20, 1337, 0, n)
+    assert_same(hist, cnt, ohist, ocnt)
+    assert int(hist.sum(dtype=np.uint64)) == cnt["increments"]
+
+
+def test_load_accumulate_read_roundtrip(buddha, oracle):
+    """-s semantics (cudabrot.cu:215-280): a loaded buffer is accumulated into, not replaced."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 1000, size=(120, 160), dtype=np.uint32)
+    ohist, _, _ = oracle.render(160, 120, 100, 20, 1337, 0, 1 << 18, hist=base.copy())
+    with buddha.Renderer(160, 120, 100, 20) as r:
+        r.load_histogram(base)
+        assert np.array_equal(r.read_histogram(), base)
+        r.render_samples(0, 1 << 18)
+        assert np.array_equal(r.read_histogram(), ohist)
+        r.clear()
+        assert r.read_histogram().sum() == 0
+        with pytest.raises(buddha.BuddhaError):
+            r.load_histogram(np.zeros(7, dtype=np.uint32))
+
+
+def test_render_seconds_semantics(buddha):
+    """-t 0 renders exactly one pass of 512*512*50 candidates (cudabrot.cu:488-491, quirk 6)."""
+    with buddha.Renderer(256, 256, 100, 20) as r:
+        done, passes = r.render_seconds(0.0)
+        assert (done, passes) == (13107200, 1)
+        assert r.counters()["candidates"] == 13107200
+        done2, passes2 = r.render_seconds(0.3, first=done)
+        assert passes2 >= 2 and done2 > 13107200
+
+
+@pytest.mark.parametrize("gamma", [1.0, 2.2, 0.5, -1.0])
+@pytest.mark.parametrize("big_endian", [False, True])
+def test_tonemap_matches_oracle_on_render(buddha, oracle, gamma, big_endian):
+    with buddha.Renderer(640, 480, 200, 20) as r:
+        r.render_samples(0, 1 << 22)
+        hist = r.read_histogram()
+        img, mx, scale = r.tonemap(gamma, big_endian)
+        assert r.last_tonemap_ms() > 0
+    oimg, omx, oscale = oracle.tonemap(hist, gamma, big_endian)
+    assert (mx, scale) == (omx, oscale)
+    assert np.array_equal(img, oimg)
+
+
+@pytest.mark.parametrize("name,side", [("kat64", (64, 64)), ("big", (32, 32)), ("zero", (16, 16))])
+@pytest.mark.parametrize("gamma", ["1.0", "2.2", "0.5", "-1"])
+def test_tonemap_matches_reference_golden_pgm(buddha, tmp_path, name, side, gamma):
+    """Against files written by the reference's own host code (tests/golden/make_golden.py);
+    `big` has counts past the 2^22-entry table, i.e. the threshold-search path."""
+    hist = np.fromfile(os.path.join(GOLDEN, "hist_%s.raw" % name), dtype="<u4").reshape(side)
+    with buddha.Renderer(side[1], side[0], 10, 0) as r:
+        r.load_histogram(hist)
+        img, mx, scale = r.tonemap(float(gamma), big_endian=True)
+    out = str(tmp_path / "o.pgm")
+    buddha.write_pgm(out, img, side[1], side[0])
+    golden = os.path.join(GOLDEN, "tonemap_%s_g%s.pgm" % (name, gamma))
+    assert open(out, "rb").read() == open(golden, "rb").read()
+    assert open(golden + ".stdout").read().strip() == "Max value: %d, scale: %f" % (mx, scale)
+
+
+def test_reference_device_code_agrees_with_oracle(oracle, tmp_path):
+    """Pins the oracle to the REFERENCE's real SASS: oracle/_ref/ref_probe runs the reference's
+    own InMainCardioid / InOrder2Bulb / IterateMandelbrot / IterateAndRecord (cudabrot.cu:284-365)
+    on this GPU over the oracle's Philox sample list."""
+    if not os.path.exists(oracle.REF_PROBE):
+        pytest.fail("oracle/_ref/ref_probe missing: run make -C oracle where /root/reference exists")
+    for (w, h, canvas, m, c, first, n) in [(1000, 1000, FULL, 100, 20, 0, 1 << 20),
+                                           (200, 100, (0.0, 1.0, 0.0, 0.5), 1000, 20, 0, 1 << 18),
+                                           (333, 77, (-1.7, 0.3, -0.123, 0.777), 3000, 50, 1 << 33,
+                                            1 << 17)]:
+        pts = np.empty((n, 2), dtype=np.float64)
+        L = oracle.lib()
+        import ctypes as C
+        re, im = C.c_double(), C.c_double()
+        for k in range(n):
+            L.oracle_sample(1337, first + k, C.byref(re), C.byref(im))
+            pts[k, 0], pts[k, 1] = re.value, im.value
+        sp, ip, hp = (str(tmp_path / f) for f in ("s.f64", "i.i32", "h.raw"))
+        pts.tofile(sp)
+        r = oracle.run_ref_probe("orbits", w, h, repr(canvas[0]), repr(canvas[1]), repr(canvas[2]),
+                                 repr(canvas[3]), m, c, sp, ip, hp)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ref_iters = np.fromfile(ip, dtype=np.int32)
+        ref_hist = np.fromfile(hp, dtype=np.uint32).reshape(h, w)
+        assert np.array_equal(ref_iters, oracle.classify(1337, first, n, m))
+        ohist, _, _ = oracle.render(w, h, m, c, 1337, first, n, canvas=canvas)
+        assert np.array_equal(ref_hist, ohist)
+
+
+def test_cli_end_to_end(buddha, oracle, tmp_path):
+    """The drop-in binary: --samples render, -s file layout, PGM bytes, resume accumulation."""
+    cli = buddha.capi.CLI_PATH
+    save, out = str(tmp_path / "state.raw"), str(tmp_path / "img.pgm")
+    args = [cli, "-w", "300", "-h", "200", "-m", "200", "-c", "10", "-g", "2.2", "-s", save,
+            "-o", out, "--samples", "500000"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Creating 300x200 image, 200 max iterations." in r.stdout
+    assert "File %s doesn't exist yet. Not loading." % save in r.stdout
+    assert "Done! Output image saved: %s" % out in r.stdout
+    ohist, _, _ = oracle.render(300, 200, 200, 10, 1337, 0, 500000)
+    assert np.array_equal(np.fromfile(save, dtype="<u4").reshape(200, 300), ohist)
+    oimg, omx, oscale = oracle.tonemap(ohist, 2.2)
+    opgm = str(tmp_path / "oracle.pgm")
+    oracle.write_pgm(opgm, oimg)
+    assert open(out, "rb").read() == open(opgm, "rb").read()
+    assert "Max value: %d, scale: %f" % (omx, oscale) in r.stdout
+    # second run resumes: loads the buffer and continues the Philox stream at the sidecar cursor
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Continuing the sample stream at index 500000." in r.stdout
+    ohist2, _, _ = oracle.render(300, 200, 200, 10, 1337, 500000, 500000, hist=ohist.copy())
+    assert np.array_equal(np.fromfile(save, dtype="<u4").reshape(200, 300), ohist2)
+    # wrong-size -s file is refused with the reference's message and exit code 1 (:239-245)
+    r = subprocess.run([cli, "-w", "301", "-h", "200", "-s", save, "--samples", "10"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1
+    assert "doesn't match the expected size of %d bytes." % (301 * 200 * 4) in r.stdout
+    # -t 0 = exactly one reference-sized pass
+    r = subprocess.run([cli, "-w", "100", "-h", "100", "-t", "0", "-o", out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "1 Buddhabrot passes took" in r.stdout
+    assert "13107200 candidate samples" in r.stdout
+
+
+def test_in_process_multi_gpu_merge(buddha, oracle):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    n = 1 << 20
+    ohist, _, _ = oracle.render(400, 300, 300, 20, 1337, 0, n)
+    rs = [buddha.Renderer(400, 300, 300, 20, device=d) for d in range(2)]
+    rs[0].render_samples(0, n // 2)
+    rs[1].render_samples(n // 2, n - n // 2)
+    buddha.merge_in_process(rs, root=0)
+    assert np.array_equal(rs[0].read_histogram(), ohist)
+    for r in rs:
+        r.close()
