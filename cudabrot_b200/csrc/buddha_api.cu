@@ -44,6 +44,8 @@ struct buddha_ctx {
   unsigned long long *d_cursor;   // offset handed out so far in the current launch
   unsigned long long *d_counters; // kCntSlots accumulators
   uint32_t *d_max;
+  OrbitSpill spill;               // grid-wide list of orbits left over by the render kernel
+  unsigned int *d_spill_next;
   uint16_t *d_gray;               // tone-mapped image, allocated on first use
   uint16_t *d_lut;
   uint32_t *d_thr;
@@ -286,6 +288,11 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCntSlots));
   CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
   CUC(cudaMalloc(&c->d_max, sizeof(uint32_t)));
+  c->spill.capacity = (unsigned)c->grid * kWarpsPerCta * kStackCap;  // every warp spills < kStackCap
+  CUC(cudaMalloc(&c->spill.entries, sizeof(double4) * c->spill.capacity));
+  CUC(cudaMalloc(&c->spill.steps, sizeof(int) * c->spill.capacity));
+  CUC(cudaMalloc(&c->spill.count, sizeof(unsigned int) * 2));
+  c->d_spill_next = c->spill.count + 1;
   CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -298,6 +305,7 @@ void buddha_destroy(buddha_ctx *c) {
   cudaSetDevice(c->params.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters); cudaFree(c->d_max);
+  cudaFree(c->spill.entries); cudaFree(c->spill.steps); cudaFree(c->spill.count);
   cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -353,8 +361,14 @@ static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     uint64_t want = (count + kChunk - 1) / kChunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
+    CU(c, cudaMemsetAsync(c->spill.count, 0, sizeof(unsigned int) * 2, c->stream));
     render_persistent_kernel<<<grid, kThreadsPerCta, 0, c->stream>>>(rp, c->d_hist, c->d_cursor,
-                                                                      c->d_counters);
+                                                                      c->d_counters, c->spill);
+    CU(c, cudaGetLastError());
+    // orbits the warps could not run with enough lanes: finished with grid-wide refill
+    orbit_drain_kernel<<<grid, kThreadsPerCta, 0, c->stream>>>(rp, c->d_hist, c->d_counters,
+                                                                c->spill, c->d_spill_next);
+    c->launches += 1;
   }
   CU(c, cudaGetLastError());
   c->candidates += count;
@@ -438,8 +452,9 @@ int buddha_get_counters(buddha_ctx *c, buddha_counters *out) {
   out->candidates = c->candidates;
   out->rejected = v[kCntRejected];
   out->hit_max = v[kCntHitMax];
-  out->too_early = v[kCntTooEarly];
   out->accepted = v[kCntAccepted];
+  // every candidate ends in exactly one class; too_early is the remainder
+  out->too_early = c->candidates - v[kCntRejected] - v[kCntHitMax] - v[kCntAccepted];
   out->escape_iters = v[kCntEscapeIters];
   out->orbit_points = v[kCntOrbitPoints];
   out->increments = v[kCntIncrements];

@@ -24,14 +24,13 @@ namespace buddha {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-constexpr int kGenPerLane = 4;                 // candidates drawn per lane per generation batch
-constexpr int kCandCap = 32 + 32 * kGenPerLane; // fresh-candidate stack (per warp)
-constexpr int kDeepCap = 96;                   // long-running escape tests (per warp)
-constexpr int kOrbCap = 64;                    // accepted samples waiting for the orbit pass
+constexpr int kStackCap = 64;                  // entries per work stack (4 stacks per warp)
 constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
-constexpr int kShortIters = 32;                // escape tests longer than this go to the deep list
-constexpr int kBlock = 8;                      // unchecked steps per deep block
-constexpr int kDeepExit = 24;                  // leave a phase when fewer lanes than this are busy
+constexpr int kShortIters = 33;                // escape tests longer than this go to the deep list
+constexpr int kShortBlock = 4;                 // per-step-tested steps per short round (33 = 1 + 8*4)
+constexpr int kBlock = 8;                      // unchecked steps per deep round
+constexpr int kShortExit = 24;                 // leave a phase when fewer lanes than this are busy
+constexpr int kDeepExit = 24;
 constexpr int kOrbExit = 16;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -239,44 +238,72 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 }
 
 // ---- the persistent renderer ----------------------------------------------------------------
+//
+// One warp is the unit of scheduling.  It owns four stacks in shared memory and moves through
+// five phases, always choosing one that can keep (nearly) all 32 lanes busy:
+//
+//   gen     draw 32 candidates (Philox), cardioid/bulb test, FIRST iteration + escape test, all in
+//           straight-line code at full lane utilisation (2/3 of all candidates escape right here);
+//           survivors are ballot-compacted onto the `short` stack.
+//   short   iterations 2..kShortIters with the exact per-step escape test, kShortBlock steps per
+//           round, per-lane refill from the `short` stack.  Escapes are classified here; samples
+//           that reach kShortIters move to the `deep` stack.
+//   deep    long escape tests: kBlock unchecked steps (4 FP64 instr each) per round, one |z|^2
+//           test per round, exact periodicity shortcut.  A lane whose round ended outside the
+//           radius-2 disc is handed to the `replay` stack with its round-start state.
+//   replay  same code as short, fed from the `replay` stack: finds the exact escape index of the
+//           handed-back samples with the per-step test; never feeds deep again.
+//   orbit   re-iterate accepted samples for exactly i+1 steps and scatter with red.global.add.
+//
+// The push graph gen->{short,orbit}, short->{deep,orbit}, deep->{replay}, replay->{orbit} is
+// acyclic and the scheduler serves the stacks in the order orbit, replay, deep, short, gen; a
+// phase starts a round only while each stack it pushes to holds < 32 entries, so with 64-entry
+// stacks nothing can overflow and some phase can always run.
+
+template <int CAP>
+struct Stack {
+  double cx[CAP], cy[CAP], x[CAP], y[CAP];
+  int it[CAP];  // iterations done (orbit stack: steps still to record)
+};
 
 struct WarpQueues {
-  double cand_cx[kCandCap], cand_cy[kCandCap];
-  double deep_cx[kDeepCap], deep_cy[kDeepCap], deep_x[kDeepCap], deep_y[kDeepCap];
-  double orb_cx[kOrbCap], orb_cy[kOrbCap], orb_x[kOrbCap], orb_y[kOrbCap];
-  int deep_it[kDeepCap];
-  int orb_n[kOrbCap];
+  Stack<kStackCap> shrt, deep, rply, orb;
+  int rply_stay[kStackCap];
 };
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
-  int cand_n, deep_n, orb_n;               // stack heights (warp-uniform)
+  int short_n, deep_n, rply_n, orb_n;      // stack heights (warp-uniform)
   unsigned long long chunk_next, chunk_end; // sample indices still owned by this warp
   bool exhausted;                          // the global cursor ran past p.end
   // per-lane event counters, flushed to global memory at every cursor grab
-  uint32_t n_rej, n_hit, n_early, n_acc, n_cyc, n_exact;
+  uint32_t n_rej, n_hit, n_acc, n_cyc, n_exact;
   uint32_t e_ref, e_exec, p_pts, p_inc;
 };
 
 __device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
-  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, ws.n_early, ws.n_acc, ws.e_ref, ws.p_pts,
+  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, 0u, ws.n_acc, ws.e_ref, ws.p_pts,
                            ws.p_inc, ws.e_exec, ws.n_cyc, ws.n_exact};
 #pragma unroll
   for (int k = 0; k < kCntSlots; k++) {
+    if (k == kCntTooEarly) continue;  // derived on the host: candidates - the other classes
     unsigned long long x = v[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
     if (lane_id() == 0 && x) atomicAdd(counters + k, x);
   }
-  ws.n_rej = ws.n_hit = ws.n_early = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
+  ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
 }
 
-// Push one entry per lane with `pred` set onto a stack; returns the slot (valid where pred).
-__device__ __forceinline__ int stack_push(bool pred, int &height) {
+// Push one entry per lane with `pred` set (ballot compaction); returns the slot where pred.
+template <int CAP>
+__device__ __forceinline__ int stack_push(Stack<CAP> &st, int &height, bool pred, double cx,
+                                          double cy, double x, double y, int it) {
   unsigned m = __ballot_sync(kFull, pred);
   int slot = height + __popc(m & lanemask_lt());
   height += __popc(m);
+  if (pred) { st.cx[slot] = cx; st.cy[slot] = cy; st.x[slot] = x; st.y[slot] = y; st.it[slot] = it; }
   return slot;
 }
 
@@ -285,19 +312,25 @@ __device__ __forceinline__ int stack_pop(bool want, int &height) {
   unsigned m = __ballot_sync(kFull, want);
   int rank = __popc(m & lanemask_lt());
   int slot = (want && rank < height) ? (height - 1 - rank) : -1;
-  int taken = min(__popc(m), height);
-  height -= taken;
+  height -= min(__popc(m), height);
   return slot;
 }
 
-// (a) sampler: draw kGenPerLane candidates per lane from the Philox stream, reject the main
-// cardioid / period-2 bulb at full lane utilisation, and stack the survivors.
-__device__ __forceinline__ void generate(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                         unsigned long long *cursor,
-                                         unsigned long long *counters) {
+__device__ __forceinline__ void push_orbit(WarpQueues &q, WarpState &ws, bool acc, double cx,
+                                           double cy, int n) {
+  if (__ballot_sync(kFull, acc) == 0u) return;
+  ws.n_acc += acc ? 1u : 0u;
+  ws.p_pts += acc ? (uint32_t)n : 0u;
+  stack_push(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
+}
+
+// (a) sampler + first iteration.  One batch = one candidate per lane.
+__device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                          unsigned long long *cursor,
+                                          unsigned long long *counters) {
   const unsigned lane = lane_id();
 #pragma unroll 1
-  for (int g = 0; g < kGenPerLane; g++) {
+  while (ws.short_n < 32 && ws.orb_n < 32) {
     if (ws.chunk_next >= ws.chunk_end) {
       if (ws.exhausted) break;
       flush_counters(ws, counters);
@@ -315,93 +348,110 @@ __device__ __forceinline__ void generate(const RenderParams &p, WarpQueues &q, W
     double cx = coord2_from_words(r.x, r.y);
     double cy = coord2_from_words(r.z, r.w);
     bool rej = rejected2(cx, cy);
-    bool keep = valid && !rej;
+    bool alive = valid && !rej;
     ws.n_rej += (valid && rej) ? 1u : 0u;
     if (p.max_it <= 0) {  // IterateMandelbrot returns max at once (cudabrot.cu:326,339,407)
-      ws.n_hit += keep ? 1u : 0u;
-      keep = false;
+      ws.n_hit += alive ? 1u : 0u;
+      continue;
     }
-    int slot = stack_push(keep, ws.cand_n);
-    if (keep) { q.cand_cx[slot] = cx; q.cand_cy[slot] = cy; }
+    double x = cx, y = cy;
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    bool esc = norm4(x, y) > 16.0;
+    ws.e_exec += alive ? 1u : 0u;
+    ws.e_ref += (alive && (esc || p.max_it == 1)) ? 1u : 0u;
+    ws.n_hit += (alive && !esc && p.max_it == 1) ? 1u : 0u;
+    push_orbit(q, ws, alive && esc && (0 >= p.min_it), cx, cy, 1);
+    stack_push(q.shrt, ws.short_n, alive && !esc && p.max_it > 1, cx, cy, x, y, 1);
   }
   __syncwarp();
 }
 
-// (b) escape test with per-lane refill: every lane owns one candidate; a lane whose candidate
-// escaped (or reached the short limit) is refilled from the candidate stack in the same round.
-// Returns when a downstream list needs service or when the sample range is exhausted and every
-// lane is idle.
+// (b) escape test with the per-step test and per-lane refill.  kReplay = false: the `short`
+// stack (iterations 2..kShortIters, then on to `deep`).  kReplay = true: the `replay` stack
+// (samples handed back by deep; they run here until they escape or reach max).
+template <bool kReplay>
 __device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                            unsigned long long *cursor,
-                                            unsigned long long *counters) {
-  const int lim = min(p.max_it, kShortIters);
+                                            bool drain) {
+  Stack<kStackCap> &src = kReplay ? q.rply : q.shrt;
+  int &src_n = kReplay ? ws.rply_n : ws.short_n;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
-  int it = 0;
+  int it = 0, stay = 0;
 #pragma unroll 1
   for (;;) {
-    unsigned need = __ballot_sync(kFull, !act);
-    if (need) {
-      if (ws.cand_n < __popc(need) && !(ws.exhausted && ws.chunk_next >= ws.chunk_end))
-        generate(p, q, ws, cursor, counters);
-      int slot = stack_pop(!act, ws.cand_n);
+    if (ws.orb_n >= 32 || (!kReplay && ws.deep_n >= 32)) break;  // keep room for 32 pushes
+    if (src_n > 0 && __ballot_sync(kFull, !act)) {
+      int slot = stack_pop(!act, src_n);
       if (slot >= 0) {
-        cx = q.cand_cx[slot]; cy = q.cand_cy[slot];
-        x = cx; y = cy; it = 0; act = true;
+        cx = src.cx[slot]; cy = src.cy[slot]; x = src.x[slot]; y = src.y[slot];
+        it = src.it[slot];
+        stay = kReplay ? q.rply_stay[slot] : kShortIters;
+        act = true;
       }
       __syncwarp();
-      if (__ballot_sync(kFull, act) == 0u) return;  // nothing left anywhere
     }
-    BUDDHA_ZSTEP(x, y, cx, cy);
-    it++;
-    bool esc = norm4(x, y) > 16.0;
-    bool fin = act && (esc || it >= lim);
-    if (__ballot_sync(kFull, fin)) {
-      bool hit = fin && !esc && (it >= p.max_it);
-      bool todeep = fin && !esc && !hit;
-      bool acc = fin && esc && (it - 1 >= p.min_it);
-      ws.n_acc += acc ? 1u : 0u;
-      ws.n_early += (fin && esc && !acc) ? 1u : 0u;
+    unsigned am = __ballot_sync(kFull, act);
+    if (am == 0u) break;
+    if (!drain && __popc(am) < kShortExit) break;
+
+    // kShortBlock steps; `alive` lanes are still before their escape / limit
+    const int allowed = min(kShortBlock, p.max_it - it);
+    bool alive = act, escd = false;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kShortBlock; k++) {
+      BUDDHA_ZSTEP(x, y, cx, cy);
+      bool e = norm4(x, y) > 16.0;
+      cnt += alive ? 1 : 0;
+      escd = escd || (alive && e);
+      alive = alive && !e && (cnt < allowed);
+    }
+    it += cnt;
+    ws.e_exec += (uint32_t)cnt;
+    bool hit = act && !escd && it >= p.max_it;
+    bool todeep = act && !escd && !hit && it >= stay;
+    if (__ballot_sync(kFull, escd || hit || todeep)) {
+      ws.e_ref += (escd || hit) ? (uint32_t)it : 0u;  // esc: i+1 = it; hit: max = it
       ws.n_hit += hit ? 1u : 0u;
-      ws.e_ref += (fin && !todeep) ? (uint32_t)it : 0u;   // esc: i+1 = it; hit: max = it
-      ws.e_exec += (fin && !todeep) ? (uint32_t)it : 0u;
-      ws.p_pts += acc ? (uint32_t)it : 0u;
-      int so = stack_push(acc, ws.orb_n);
-      if (acc) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = cx; q.orb_y[so] = cy; q.orb_n[so] = it; }
-      int sd = stack_push(todeep, ws.deep_n);
-      if (todeep) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
-      if (fin) { act = false; cx = cy = x = y = 0.0; }
-      if (ws.orb_n >= 32 || ws.deep_n >= 32) break;
+      push_orbit(q, ws, escd && (it - 1 >= p.min_it), cx, cy, it);
+      if (todeep && (kReplay || !(norm4(cx, cy) <= 15.99) || it + kBlock > p.max_it)) {
+        // replayed samples never go back to deep; |c| too close to 2 for deep's no-re-entry
+        // argument; or no room for a full unchecked round before max: per-step test to the end
+        stay = p.max_it;
+        todeep = false;
+      }
+      if (!kReplay && __ballot_sync(kFull, todeep))
+        stack_push(q.deep, ws.deep_n, todeep, cx, cy, x, y, it);
+      if (escd || hit || todeep) { act = false; cx = cy = x = y = 0.0; it = 0; }
     }
   }
-  // suspend: the candidates still in flight continue in the deep list from their current state
-  int sd = stack_push(act, ws.deep_n);
-  if (act) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
+  // suspend: lanes still in flight go back on their stack
+  if (__ballot_sync(kFull, act)) {
+    int ss = stack_push(src, src_n, act, cx, cy, x, y, it);
+    if (kReplay && act) q.rply_stay[ss] = stay;
+  }
   __syncwarp();
 }
 
-// (c) long escape tests, re-queued through the shared-memory list so that all 32 lanes iterate.
-// Each round runs kBlock unchecked steps (4 FP64 instr each) and tests |z|^2 once.  Because
+// (c) long escape tests.  Each round runs kBlock unchecked steps and tests |z|^2 once.  Because
 // |c| <= 2 here, an orbit that leaves the radius-2 disc cannot re-enter it,
-// so "escaped somewhere in the block" <=> "escaped at the end of the block"; the block is then
-// replayed from its saved start with the per-step test to get the exact iteration index.
-// A state that repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (shortcut).
+// so "escaped somewhere in the round" <=> "outside at the end of the round".  A state that
+// repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (exact shortcut).
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            bool drain) {
-  bool act = false, slow = false;
+  bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
-  int it = 0;
+  int it = 0, it0 = 0;
+  unsigned age = 0;  // rounds since this lane's sample was loaded (Brent checkpoint schedule)
 #pragma unroll 1
   for (;;) {
-    if (ws.orb_n >= 32) break;  // keep room for 32 pushes
-    unsigned need = __ballot_sync(kFull, !act);
-    if (need && ws.deep_n > 0) {
+    if (ws.rply_n >= 32) break;  // keep room for 32 hand-backs
+    if (ws.deep_n > 0 && __ballot_sync(kFull, !act)) {
       int slot = stack_pop(!act, ws.deep_n);
       if (slot >= 0) {
-        cx = q.deep_cx[slot]; cy = q.deep_cy[slot];
-        x = q.deep_x[slot]; y = q.deep_y[slot]; it = q.deep_it[slot];
-        rx = x; ry = y;
-        slow = !(norm4(cx, cy) <= 15.99);  // |c| too close to 2: always use the per-step test
+        cx = q.deep.cx[slot]; cy = q.deep.cy[slot];
+        x = q.deep.x[slot]; y = q.deep.y[slot]; it = q.deep.it[slot];
+        rx = x; ry = y; it0 = it; age = 0;
         act = true;
       }
       __syncwarp();
@@ -410,117 +460,176 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
     if (am == 0u) break;
     if (!drain && __popc(am) < kDeepExit) break;
 
-    const double x0 = x, y0 = y;
-    const int rem = p.max_it - it;
-    const bool fastok = act && !slow && rem >= kBlock;
-#pragma unroll
-    for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
-    const bool esc8 = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
-    bool replay = act && (!fastok || esc8);
-    bool esc = false, cyc = false;
-    if (fastok && !esc8) {
-      it += kBlock;
-      if (p.shortcut) {
-        if (__double_as_longlong(x) == __double_as_longlong(rx) &&
-            __double_as_longlong(y) == __double_as_longlong(ry)) {
-          cyc = true;
-        } else if ((it & (it - 1)) == 0) {
-          rx = x; ry = y;
-        }
-      }
-    }
-    if (__ballot_sync(kFull, replay)) {
-      if (replay) {
-        x = x0; y = y0;
-        const int n = min(kBlock, rem);
+    bool fin;
 #pragma unroll 1
-        for (int k = 0; k < n; k++) {
-          BUDDHA_ZSTEP(x, y, cx, cy);
-          it++;
-          if (norm4(x, y) > 16.0) { esc = true; break; }
-        }
-        ws.e_exec += fastok ? (uint32_t)kBlock : 0u;  // the unchecked pass that was discarded
+    do {  // rounds without bookkeeping until some lane needs attention
+      const double x0 = x, y0 = y;
+#pragma unroll
+      for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
+      const bool out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
+      it += kBlock;
+      bool cyc = false;
+      if (p.shortcut) {
+        cyc = __double_as_longlong(x) == __double_as_longlong(rx) &&
+              __double_as_longlong(y) == __double_as_longlong(ry);
+        age++;
+        if ((age & (age - 1)) == 0) { rx = x; ry = y; }  // new checkpoint at 1, 2, 4, 8, ... rounds
       }
-    }
-    bool hit = act && !esc && (cyc || it >= p.max_it);
-    bool fin = act && (esc || hit);
-    if (__ballot_sync(kFull, fin)) {
-      bool acc = esc && (it - 1 >= p.min_it);
-      ws.n_acc += acc ? 1u : 0u;
-      ws.n_early += (esc && !acc) ? 1u : 0u;
+      const bool tail = it + kBlock > p.max_it;  // no room for another full round
+      fin = act && (out || cyc || tail);
+      if (act && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
+      if (act && cyc && !out) it |= 0x40000000;           // mark: proven periodic
+    } while (__ballot_sync(kFull, fin) == 0u);
+
+    {
+      const bool cyc = (it & 0x40000000) != 0;
+      it &= 0x3fffffff;
+      const bool hit = fin && (cyc || it >= p.max_it);   // periodic, or ran all max iterations
+      const bool back = fin && !hit;                     // escaped in the round, or a short tail
+      ws.e_exec += fin ? (uint32_t)(it - it0) + ((back && it + kBlock <= p.max_it) ? kBlock : 0u) : 0u;
       ws.n_hit += hit ? 1u : 0u;
       ws.n_cyc += (hit && it < p.max_it) ? 1u : 0u;
-      ws.e_ref += esc ? (uint32_t)it : (hit ? (uint32_t)p.max_it : 0u);
-      ws.e_exec += fin ? (uint32_t)it : 0u;
-      ws.p_pts += acc ? (uint32_t)it : 0u;
-      int so = stack_push(acc, ws.orb_n);
-      if (acc) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = cx; q.orb_y[so] = cy; q.orb_n[so] = it; }
-      if (fin) { act = false; cx = cy = x = y = 0.0; it = 0; }
+      ws.e_ref += hit ? (uint32_t)p.max_it : 0u;
+      if (__ballot_sync(kFull, back)) {
+        int ss = stack_push(q.rply, ws.rply_n, back, cx, cy, x, y, it);
+        // an escape is certain within the next kBlock steps; a tail just runs out at max
+        if (back) q.rply_stay[ss] = (it + kBlock <= p.max_it) ? it + kBlock : p.max_it;
+      }
+      if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it = 0; it0 = 0; }
     }
   }
-  int sd = stack_push(act, ws.deep_n);
-  if (act) { q.deep_cx[sd] = cx; q.deep_cy[sd] = cy; q.deep_x[sd] = x; q.deep_y[sd] = y; q.deep_it[sd] = it; }
+  if (__ballot_sync(kFull, act)) {
+    ws.e_exec += act ? (uint32_t)(it - it0) : 0u;
+    stack_push(q.deep, ws.deep_n, act, cx, cy, x, y, it);
+  }
   __syncwarp();
 }
 
 // (d) orbit pass: re-iterate accepted samples for exactly i+1 steps (no escape test needed: the
 // count is known), scatter every point with a fire-and-forget red.global.add.u32.
+struct OrbitLane {
+  bool act;
+  double cx, cy, x, y;
+  int n;
+};
+
+__device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
+                                           uint32_t *hist) {
+  BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
+  if (o.act) {
+    bool exact = false;
+    bool in = p.fast_bin ? bin_point(o.x, o.y, p, hist, &exact)
+                         : (exact = true, bin_exact(o.x, o.y, p, hist));
+    ws.p_inc += in ? 1u : 0u;
+    ws.n_exact += exact ? 1u : 0u;
+    if (--o.n == 0) { o.act = false; o.cx = o.cy = o.x = o.y = 0.0; }
+  }
+}
+
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                            uint32_t *hist, bool drain) {
-  bool act = false;
-  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
-  int n = 0;
+                                            uint32_t *hist) {
+  OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
 #pragma unroll 1
   for (;;) {
-    unsigned need = __ballot_sync(kFull, !act);
-    if (need && ws.orb_n > 0) {
-      int slot = stack_pop(!act, ws.orb_n);
+    if (ws.orb_n > 0 && __ballot_sync(kFull, !o.act)) {
+      int slot = stack_pop(!o.act, ws.orb_n);
       if (slot >= 0) {
-        cx = q.orb_cx[slot]; cy = q.orb_cy[slot];
-        x = q.orb_x[slot]; y = q.orb_y[slot]; n = q.orb_n[slot];
-        act = true;
+        o.cx = q.orb.cx[slot]; o.cy = q.orb.cy[slot];
+        o.x = q.orb.x[slot]; o.y = q.orb.y[slot]; o.n = q.orb.it[slot];
+        o.act = true;
       }
       __syncwarp();
     }
-    unsigned am = __ballot_sync(kFull, act);
-    if (am == 0u) break;
-    if (!drain && __popc(am) < kOrbExit) break;
-    BUDDHA_ZSTEP(x, y, cx, cy);
-    if (act) {
-      bool exact = false;
-      bool in = p.fast_bin ? bin_point(x, y, p, hist, &exact) : (exact = true, bin_exact(x, y, p, hist));
-      ws.p_inc += in ? 1u : 0u;
-      ws.n_exact += exact ? 1u : 0u;
-      if (--n == 0) { act = false; cx = cy = x = y = 0.0; }
-    }
+    unsigned am = __ballot_sync(kFull, o.act);
+    if (__popc(am) < kOrbExit) break;
+    orbit_step(p, o, ws, hist);
   }
-  int so = stack_push(act, ws.orb_n);
-  if (act) { q.orb_cx[so] = cx; q.orb_cy[so] = cy; q.orb_x[so] = x; q.orb_y[so] = y; q.orb_n[so] = n; }
+  if (__ballot_sync(kFull, o.act))
+    stack_push(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
 }
+
+// Orbit entries a warp could not run with enough lanes are spilled to a grid-wide list and
+// finished by orbit_drain_kernel, where lanes refill from the whole grid's leftovers.
+struct OrbitSpill {
+  double4 *entries;          // (cx, cy, x, y)
+  int *steps;                // remaining steps
+  unsigned int *count;       // entries written
+  unsigned int capacity;
+};
 
 __global__ void __launch_bounds__(kThreadsPerCta)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
-                         unsigned long long *__restrict__ counters) {
+                         unsigned long long *__restrict__ counters, OrbitSpill spill) {
   __shared__ WarpQueues queues[kWarpsPerCta];
   WarpQueues &q = queues[threadIdx.x >> 5];
   WarpState ws;
-  ws.cand_n = ws.deep_n = ws.orb_n = 0;
+  ws.short_n = ws.deep_n = ws.rply_n = ws.orb_n = 0;
   ws.chunk_next = ws.chunk_end = 0;
   ws.exhausted = false;
-  ws.n_rej = ws.n_hit = ws.n_early = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
+  ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
 
 #pragma unroll 1
   for (;;) {
-    if (ws.orb_n >= 32) { orbit_phase(p, q, ws, hist, false); continue; }
+    // strict priority along the push graph: a phase is reached only when every stack it pushes
+    // to holds < 32 entries
+    if (ws.orb_n >= 32) { orbit_phase(p, q, ws, hist); continue; }
+    if (ws.rply_n >= 32) { short_phase<true>(p, q, ws, false); continue; }
     if (ws.deep_n >= 32) { deep_phase(p, q, ws, false); continue; }
-    bool more = !(ws.exhausted && ws.chunk_next >= ws.chunk_end) || ws.cand_n > 0;
-    if (more) { short_phase(p, q, ws, cursor, counters); continue; }
+    if (ws.short_n >= 32) { short_phase<false>(p, q, ws, false); continue; }
+    if (!(ws.exhausted && ws.chunk_next >= ws.chunk_end)) { gen_phase(p, q, ws, cursor, counters); continue; }
+    // the sample range is used up: run the partial stacks dry
+    if (ws.rply_n > 0) { short_phase<true>(p, q, ws, true); continue; }
+    if (ws.short_n > 0) { short_phase<false>(p, q, ws, true); continue; }
     if (ws.deep_n > 0) { deep_phase(p, q, ws, true); continue; }
-    if (ws.orb_n > 0) { orbit_phase(p, q, ws, hist, true); continue; }
     break;
+  }
+  // leftovers (< 32 accepted samples): hand them to the grid-wide list
+  if (ws.orb_n > 0) {
+    unsigned base = 0;
+    if (lane_id() == 0) base = atomicAdd(spill.count, (unsigned)ws.orb_n);
+    base = __shfl_sync(kFull, base, 0);
+    for (int k = lane_id(); k < ws.orb_n; k += 32) {
+      unsigned dst = base + k;
+      if (dst < spill.capacity) {
+        spill.entries[dst] = make_double4(q.orb.cx[k], q.orb.cy[k], q.orb.x[k], q.orb.y[k]);
+        spill.steps[dst] = q.orb.it[k];
+      }
+    }
+  }
+  flush_counters(ws, counters);
+}
+
+// Finishes the spilled orbits: every lane pulls the next entry from the grid-wide list.
+__global__ void __launch_bounds__(kThreadsPerCta)
+orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
+                   unsigned long long *__restrict__ counters, OrbitSpill spill,
+                   unsigned int *__restrict__ next) {
+  const unsigned total = min(*spill.count, spill.capacity);
+  WarpState ws;
+  ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
+  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+  OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
+  bool more = true;
+#pragma unroll 1
+  for (;;) {
+    unsigned need = __ballot_sync(kFull, !o.act);
+    if (need && more) {
+      unsigned base = 0;
+      if (lane_id() == 0) base = atomicAdd(next, (unsigned)__popc(need));
+      base = __shfl_sync(kFull, base, 0);
+      unsigned idx = base + __popc(need & lanemask_lt());
+      if (!o.act && idx < total) {
+        double4 e = spill.entries[idx];
+        o.cx = e.x; o.cy = e.y; o.x = e.z; o.y = e.w; o.n = spill.steps[idx];
+        o.act = true;
+      }
+      more = base + __popc(need) < total;
+    }
+    if (__ballot_sync(kFull, o.act) == 0u) break;
+    orbit_step(p, o, ws, hist);
   }
   flush_counters(ws, counters);
 }

@@ -8,22 +8,22 @@ nproc >> gpurun_out/gpu.txt
 for what in "$@"; do
 case $what in
 tests)
-  python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.txt ;;
+  timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.txt; tail -25 gpurun_out/pytest_gpu.txt ;;
 smoke)
-  python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/smoke.txt ;;
+  timeout -s KILL 120 python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/smoke.txt ;;
 bench)
-  python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  timeout -s KILL 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
   tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json ;;
 benchref)
-  python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  timeout -s KILL 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
   cat gpurun_out/bench_ref.json ;;
 ncu)
   ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --skip-baselines \
-      --samples-per-step 268435456 > gpurun_out/ncu_bench.log 2>&1
+      --log-file gpurun_out/launches.csv timeout -s KILL 300 python bench.py --steps 2 --warmup 1 --skip-baselines \
+      --samples-per-step 1073741824 > gpurun_out/ncu_bench.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:render_persistent -s 1 -c 1 \
-      -f -o gpurun_out/prof_render python bench.py --steps 1 --warmup 1 --skip-baselines \
-      --samples-per-step 268435456 > gpurun_out/ncu_full.log 2>&1
+      -f -o gpurun_out/prof_render timeout -s KILL 600 python bench.py --steps 1 --warmup 1 --skip-baselines \
+      --samples-per-step 1073741824 > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log ;;
 esac
 done
