@@ -1,0 +1,16 @@
+#!/bin/bash
+# Runs bench.py on every BASELINE.json workload (1 GPU, short) and collects the JSON lines.
+mkdir -p gpurun_out
+: > gpurun_out/workloads.jsonl
+for wl in cfg1 cfg2 cfg3 cfg3_m20000 cfg4 cfg5a cfg5b cfg5c; do
+  timeout -s KILL 300 python bench.py --workload $wl --steps 2 --warmup 1 --skip-baselines \
+    --samples-per-step ${1:-4294967296} >> gpurun_out/workloads.jsonl 2>> gpurun_out/workloads.err
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/workloads.jsonl'):
+    d=json.loads(l); c=d['counters']; S=d['config']['samples_per_step_per_gpu']*d['steps']
+    print("%-12s %.3e samples/s  %.3e pts/s  e2e %.3e  frac %.2f  exec/S %.1f ref/S %.1f P/S %.3f exact %.4f ms/step %.1f" % (
+        d['config']['workload'].split(':')[0], d['value'], d['orbit_points_per_s'], d['e2e']['value'], d['roofline']['frac'],
+        c['executed_iters']/S, c['escape_iters']/S, c['orbit_points']/S, c['exact_bins']/max(c['orbit_points'],1), d['ms_per_step']))
+PY
