@@ -99,15 +99,14 @@ def time_cpu_oracle(wl, budget_s=12.0):
     """cpu_baseline: the OpenMP oracle on this host's cores, on a bounded sample of the workload."""
     import oracle_lib as O
     w, h, m, c, canvas, _ = wl
-    n = 1 << 20
-    t0 = time.perf_counter()
-    O.render(w, h, m, c, 1337, 1 << 50, n, canvas=canvas)
-    probe = time.perf_counter() - t0
-    rate = n / max(probe, 1e-3)
-    n = int(min(max(rate * budget_s, 1 << 20), 1 << 30))
-    t0 = time.perf_counter()
-    _, cnt, threads = O.render(w, h, m, c, 1337, 0, n, canvas=canvas)
-    dt = time.perf_counter() - t0
+    n, dt = 1 << 22, 0.0
+    for _ in range(3):  # grow the sample until it is worth ~budget_s of CPU work
+        t0 = time.perf_counter()
+        _, cnt, threads = O.render(w, h, m, c, 1337, 0, n, canvas=canvas)
+        dt = time.perf_counter() - t0
+        if dt >= 0.6 * budget_s or n >= (1 << 31):
+            break
+        n = int(min(n * max(budget_s / max(dt, 1e-3), 2.0), 1 << 31))
     return {"value": n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
             "sample": "%d samples of the same workload (seed 1337, indices 0..), %.1f s, OpenMP "
                       "oracle/liboracle.so" % (n, dt),
@@ -344,6 +343,15 @@ def native_arm(args, wl, rank, world, local_rank):
         "clocks": clocks, "roofline": roofline,
     }
 
+    # second roofline: red.global.add.u32 rate vs a probe scattering over the same footprint
+    red_peak = r.probe_red_peak(cells * 4)
+    line["roofline_red"] = {
+        "bound": "l2-red", "unit": "Gred/s", "achieved": cnt["increments"] * scale / t_s / 1e9,
+        "peak": red_peak / 1e9, "frac": cnt["increments"] * scale / t_s / red_peak,
+        "footprint_bytes": cells * 4,
+        "peak_source": "in-run probe: red.global.add.u32 to uniformly random cells of an array of "
+                       "the histogram's size (buddha_probe_red_peak)",
+        "algorithmic_bytes_per_increment": 4}
     if world == 1 and not args.skip_baselines:
         r.close()
         line["cpu_baseline"] = time_cpu_oracle(wl)
