@@ -28,7 +28,7 @@ constexpr int kStackCap = 64;                  // entries per work stack (4 stac
 constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
 constexpr int kShortIters = 33;                // escape tests longer than this go to the deep list
 constexpr int kShortBlock = 4;                 // per-step-tested steps per short round (33 = 1 + 8*4)
-constexpr int kBlock = 8;                      // unchecked steps per deep round
+constexpr int kBlock = 16;                     // unchecked steps per deep round
 constexpr int kShortExit = 24;                 // leave a phase when fewer lanes than this are busy
 constexpr int kDeepExit = 24;
 constexpr int kOrbExit = 16;
@@ -252,13 +252,14 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 //           test per round, exact periodicity shortcut.  A lane whose round ended outside the
 //           radius-2 disc is handed to the `replay` stack with its round-start state.
 //   replay  same code as short, fed from the `replay` stack: finds the exact escape index of the
-//           handed-back samples with the per-step test; never feeds deep again.
+//           handed-back samples with the per-step test; also continues suspended short lanes.
 //   orbit   re-iterate accepted samples for exactly i+1 steps and scatter with red.global.add.
 //
-// The push graph gen->{short,orbit}, short->{deep,orbit}, deep->{replay}, replay->{orbit} is
-// acyclic and the scheduler serves the stacks in the order orbit, replay, deep, short, gen; a
-// phase starts a round only while each stack it pushes to holds < 32 entries, so with 64-entry
-// stacks nothing can overflow and some phase can always run.
+// Pushes: gen->{short,orbit}, short->{deep,orbit,replay}, deep->{replay}, replay->{orbit,deep}.
+// The scheduler serves the stacks in the order orbit, replay, deep, short, gen; a phase starts a
+// round only while each stack it MUST push to holds < 32 entries (replay only feeds deep while
+// deep has room, otherwise its lanes keep stepping), so with 64-entry stacks nothing can overflow
+// and some phase can always run.
 
 template <int CAP>
 struct Stack {
@@ -266,8 +267,25 @@ struct Stack {
   int it[CAP];  // iterations done (orbit stack: steps still to record)
 };
 
+// `short` holds fresh candidates only (z after the first step is recomputed from c at the pop:
+// 4 FP64 instructions instead of 20 B of shared memory per entry); a short lane that has to be
+// suspended goes to `replay`, which keeps the full state.
+struct ShortStack {
+  double cx[kStackCap], cy[kStackCap];
+};
+
+// `deep` entries carry their Brent checkpoint, so suspending a lane does not restart the
+// periodicity search (long cycles need long uninterrupted windows).
+struct DeepStack {
+  double cx[kStackCap], cy[kStackCap], x[kStackCap], y[kStackCap], rx[kStackCap], ry[kStackCap];
+  int it[kStackCap];
+  unsigned age[kStackCap];
+};
+
 struct WarpQueues {
-  Stack<kStackCap> shrt, deep, rply, orb;
+  ShortStack shrt;
+  DeepStack deep;
+  Stack<kStackCap> rply, orb;
   int rply_stay[kStackCap];
 };
 
@@ -361,31 +379,58 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     ws.e_ref += (alive && (esc || p.max_it == 1)) ? 1u : 0u;
     ws.n_hit += (alive && !esc && p.max_it == 1) ? 1u : 0u;
     push_orbit(q, ws, alive && esc && (0 >= p.min_it), cx, cy, 1);
-    stack_push(q.shrt, ws.short_n, alive && !esc && p.max_it > 1, cx, cy, x, y, 1);
+    {
+      const bool keep = alive && !esc && p.max_it > 1;
+      unsigned m = __ballot_sync(kFull, keep);
+      int slot = ws.short_n + __popc(m & lanemask_lt());
+      ws.short_n += __popc(m);
+      if (keep) { q.shrt.cx[slot] = cx; q.shrt.cy[slot] = cy; }
+    }
   }
   __syncwarp();
 }
 
-// (b) escape test with the per-step test and per-lane refill.  kReplay = false: the `short`
-// stack (iterations 2..kShortIters, then on to `deep`).  kReplay = true: the `replay` stack
-// (samples handed back by deep; they run here until they escape or reach max).
+__device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pred, double cx,
+                                          double cy, double x, double y, double rx, double ry,
+                                          int it, unsigned age) {
+  unsigned m = __ballot_sync(kFull, pred);
+  if (m == 0u) return;
+  int slot = ws.deep_n + __popc(m & lanemask_lt());
+  ws.deep_n += __popc(m);
+  if (pred) {
+    q.deep.cx[slot] = cx; q.deep.cy[slot] = cy; q.deep.x[slot] = x; q.deep.y[slot] = y;
+    q.deep.rx[slot] = rx; q.deep.ry[slot] = ry; q.deep.it[slot] = it; q.deep.age[slot] = age;
+  }
+}
+
+// (b) escape test with the per-step test and per-lane refill.  kReplay = false: fresh candidates
+// from the `short` stack (iterations 2..kShortIters, then on to `deep`).  kReplay = true: the
+// `replay` stack (samples handed back by deep, which run here until they escape or reach max,
+// and suspended short lanes).
 template <bool kReplay>
 __device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                             bool drain) {
-  Stack<kStackCap> &src = kReplay ? q.rply : q.shrt;
   int &src_n = kReplay ? ws.rply_n : ws.short_n;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
   int it = 0, stay = 0;
 #pragma unroll 1
   for (;;) {
-    if (ws.orb_n >= 32 || (!kReplay && ws.deep_n >= 32)) break;  // keep room for 32 pushes
+    // keep room for 32 pushes per target; replay may run with deep full (its lanes then wait)
+    if (ws.orb_n >= 32 || (!kReplay && ws.deep_n >= 32)) break;
+    const bool deep_room = ws.deep_n < 32;
     if (src_n > 0 && __ballot_sync(kFull, !act)) {
       int slot = stack_pop(!act, src_n);
       if (slot >= 0) {
-        cx = src.cx[slot]; cy = src.cy[slot]; x = src.x[slot]; y = src.y[slot];
-        it = src.it[slot];
-        stay = kReplay ? q.rply_stay[slot] : kShortIters;
+        if (kReplay) {
+          cx = q.rply.cx[slot]; cy = q.rply.cy[slot]; x = q.rply.x[slot]; y = q.rply.y[slot];
+          it = q.rply.it[slot]; stay = q.rply_stay[slot];
+        } else {
+          cx = q.shrt.cx[slot]; cy = q.shrt.cy[slot];
+          x = cx; y = cy;
+          BUDDHA_ZSTEP(x, y, cx, cy);  // the first step again (gen did not keep z1)
+          it = 1; stay = kShortIters;
+        }
         act = true;
       }
       __syncwarp();
@@ -414,21 +459,21 @@ __device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q
       ws.e_ref += (escd || hit) ? (uint32_t)it : 0u;  // esc: i+1 = it; hit: max = it
       ws.n_hit += hit ? 1u : 0u;
       push_orbit(q, ws, escd && (it - 1 >= p.min_it), cx, cy, it);
-      if (todeep && (kReplay || !(norm4(cx, cy) <= 15.99) || it + kBlock > p.max_it)) {
-        // replayed samples never go back to deep; |c| too close to 2 for deep's no-re-entry
-        // argument; or no room for a full unchecked round before max: per-step test to the end
+      if (todeep && (!(norm4(cx, cy) <= 15.99) || it + kBlock > p.max_it)) {
+        // |c| too close to 2 for deep's no-re-entry argument, or no room for a full unchecked
+        // round before max: per-step test to the end
         stay = p.max_it;
         todeep = false;
       }
-      if (!kReplay && __ballot_sync(kFull, todeep))
-        stack_push(q.deep, ws.deep_n, todeep, cx, cy, x, y, it);
+      todeep = todeep && deep_room;  // replay with deep full: keep stepping here, retry later
+      push_deep(q, ws, todeep, cx, cy, x, y, x, y, it, 0u);
       if (escd || hit || todeep) { act = false; cx = cy = x = y = 0.0; it = 0; }
     }
   }
-  // suspend: lanes still in flight go back on their stack
+  // suspend: lanes still in flight go to the replay stack with their full state
   if (__ballot_sync(kFull, act)) {
-    int ss = stack_push(src, src_n, act, cx, cy, x, y, it);
-    if (kReplay && act) q.rply_stay[ss] = stay;
+    int ss = stack_push(q.rply, ws.rply_n, act, cx, cy, x, y, it);
+    if (act) q.rply_stay[ss] = stay;
   }
   __syncwarp();
 }
@@ -439,10 +484,14 @@ __device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q
 // repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (exact shortcut).
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            bool drain) {
+  const int max_it = p.max_it;
+  const bool shortcut = p.shortcut != 0;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
-  int it = 0, it0 = 0;
-  unsigned age = 0;  // rounds since this lane's sample was loaded (Brent checkpoint schedule)
+  int it0 = 0;          // iterations done when this lane's sample was loaded ...
+  unsigned age0 = 0;    // ... and its age then: it = it0 + (age - age0) * kBlock
+  unsigned age = 0;     // rounds this sample has spent in deep (Brent checkpoint schedule)
+  unsigned last = 0;    // the age after which no further full round fits below max_it
 #pragma unroll 1
   for (;;) {
     if (ws.rply_n >= 32) break;  // keep room for 32 hand-backs
@@ -450,8 +499,9 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       int slot = stack_pop(!act, ws.deep_n);
       if (slot >= 0) {
         cx = q.deep.cx[slot]; cy = q.deep.cy[slot];
-        x = q.deep.x[slot]; y = q.deep.y[slot]; it = q.deep.it[slot];
-        rx = x; ry = y; it0 = it; age = 0;
+        x = q.deep.x[slot]; y = q.deep.y[slot]; it0 = q.deep.it[slot];
+        rx = q.deep.rx[slot]; ry = q.deep.ry[slot]; age0 = age = q.deep.age[slot];
+        last = age0 + (unsigned)(max_it - it0) / kBlock;  // >= age0 + 1 (it0 + kBlock <= max)
         act = true;
       }
       __syncwarp();
@@ -460,47 +510,47 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
     if (am == 0u) break;
     if (!drain && __popc(am) < kDeepExit) break;
 
-    bool fin;
+    // rounds without bookkeeping until some lane needs attention
+    double x0, y0;
+    bool out, same_x, tail;
 #pragma unroll 1
-    do {  // rounds without bookkeeping until some lane needs attention
-      const double x0 = x, y0 = y;
+    for (;;) {
+      x0 = x; y0 = y;
 #pragma unroll
       for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
-      const bool out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
-      it += kBlock;
-      bool cyc = false;
-      if (p.shortcut) {
-        cyc = __double_as_longlong(x) == __double_as_longlong(rx) &&
-              __double_as_longlong(y) == __double_as_longlong(ry);
-        age++;
-        if ((age & (age - 1)) == 0) { rx = x; ry = y; }  // new checkpoint at 1, 2, 4, 8, ... rounds
-      }
-      const bool tail = it + kBlock > p.max_it;  // no room for another full round
-      fin = act && (out || cyc || tail);
-      if (act && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
-      if (act && cyc && !out) it |= 0x40000000;           // mark: proven periodic
-    } while (__ballot_sync(kFull, fin) == 0u);
-
+      out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
+      const unsigned prev = age++;
+      same_x = shortcut && __double_as_longlong(x) == __double_as_longlong(rx);
+      tail = age == last;
+      const bool fin = act && (out || same_x || tail);
+      if (__ballot_sync(kFull, fin)) break;
+      if ((age & prev) == 0u) { rx = x; ry = y; }  // new checkpoint after 1, 2, 4, 8, ... rounds
+    }
     {
-      const bool cyc = (it & 0x40000000) != 0;
-      it &= 0x3fffffff;
-      const bool hit = fin && (cyc || it >= p.max_it);   // periodic, or ran all max iterations
-      const bool back = fin && !hit;                     // escaped in the round, or a short tail
-      ws.e_exec += fin ? (uint32_t)(it - it0) + ((back && it + kBlock <= p.max_it) ? kBlock : 0u) : 0u;
+      // the checkpoint update of the final round was skipped by the break: compare first
+      const bool cyc = same_x && __double_as_longlong(y) == __double_as_longlong(ry);
+      if ((age & (age - 1u)) == 0u) { rx = x; ry = y; }
+      const bool fin = act && (out || cyc || tail);
+      int it = it0 + (int)((age - age0) * kBlock);
+      if (fin && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
+      const bool hit = fin && !out && (cyc || it >= max_it);  // periodic, or ran all max iterations
+      const bool back = fin && !hit;                    // escaped in the round, or a short tail
+      ws.e_exec += fin ? (uint32_t)(it - it0) + (out ? (uint32_t)kBlock : 0u) : 0u;
       ws.n_hit += hit ? 1u : 0u;
-      ws.n_cyc += (hit && it < p.max_it) ? 1u : 0u;
-      ws.e_ref += hit ? (uint32_t)p.max_it : 0u;
+      ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
+      ws.e_ref += hit ? (uint32_t)max_it : 0u;
       if (__ballot_sync(kFull, back)) {
         int ss = stack_push(q.rply, ws.rply_n, back, cx, cy, x, y, it);
         // an escape is certain within the next kBlock steps; a tail just runs out at max
-        if (back) q.rply_stay[ss] = (it + kBlock <= p.max_it) ? it + kBlock : p.max_it;
+        if (back) q.rply_stay[ss] = out ? it + kBlock : max_it;
       }
-      if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it = 0; it0 = 0; }
+      if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
     }
   }
-  if (__ballot_sync(kFull, act)) {
+  {
+    int it = it0 + (int)((age - age0) * kBlock);
     ws.e_exec += act ? (uint32_t)(it - it0) : 0u;
-    stack_push(q.deep, ws.deep_n, act, cx, cy, x, y, it);
+    push_deep(q, ws, act, cx, cy, x, y, rx, ry, it, age);  // keeps the checkpoint and its schedule
   }
   __syncwarp();
 }
