@@ -46,6 +46,19 @@ struct buddha_ctx {
   uint32_t *d_max;
   OrbitSpill spill;               // grid-wide list of orbits left over by the render kernel
   unsigned int *d_spill_next;
+  // tile-binned scatter (histograms far beyond L2), see scatter() in buddha_kernels.cuh
+  bool tiled, tile_calibrated;
+  int tile_shift, n_tiles;
+  uint32_t tile_warps;            // warps of the full grid = lists per tile
+  size_t n_lists, tile_smem;
+  uint32_t *d_tcount, *d_tcap, *d_pool;   // d_tcount / d_pool hold two buffers each
+  cudaStream_t apply_stream;              // apply_tiles_kernel of launch k overlaps render k+1
+  cudaEvent_t ev_rendered, ev_applied[2];
+  bool apply_pending[2];
+  int tile_buf;
+  unsigned long long *d_tbase;
+  size_t pool_entries;
+  double tile_pts_per_sample;
   uint16_t *d_gray;               // tone-mapped image, allocated on first use
   uint16_t *d_lut;
   uint32_t *d_thr;
@@ -294,6 +307,53 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaMalloc(&c->spill.count, sizeof(unsigned int) * 2));
   c->d_spill_next = c->spill.count + 1;
   CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
+  {
+    // tile-binned scatter: on for histograms >= 768 MB (config 3: 1.6 GB), or when forced (tests)
+    const char *e;
+    size_t min_mb = 768;
+    if ((e = getenv("BUDDHA_TILE_MIN_MB"))) min_mb = (size_t)strtoull(e, nullptr, 10);
+    const bool forced = (p->flags & BUDDHA_F_FORCE_TILED) != 0;
+    c->tiled = !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
+               (forced || c->cells * sizeof(uint32_t) >= (min_mb << 20));
+    if (c->tiled) {
+      c->tile_shift = forced ? 12 : 24;  // 16 KB test tiles / 64 MB production tiles
+      if ((e = getenv("BUDDHA_TILE_SHIFT"))) c->tile_shift = atoi(e);
+      if (c->tile_shift < 8 || c->tile_shift > 28) c->tile_shift = 24;
+      c->n_tiles = (int)((c->cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
+      c->tile_smem = (size_t)c->n_tiles * kWarpsPerCta * sizeof(uint32_t);
+      if (c->tile_smem > 8192) {  // > 512 tiles: not a case tiling is meant for
+        buddha_destroy(c);
+        return fail(nullptr, BUDDHA_EINVAL, "tile-binned scatter supports at most 512 tiles");
+      }
+      // the per-warp append counters are dynamic shared memory: keep the grid one resident wave
+      int per_sm_tiled = 0;
+      CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tiled, render_persistent_kernel,
+                                                        kThreadsPerCta, c->tile_smem));
+      if (per_sm_tiled >= 1) c->grid = per_sm_tiled * c->sm_count;
+      c->tile_warps = (uint32_t)c->grid * kWarpsPerCta;
+      c->n_lists = (size_t)c->n_tiles * c->tile_warps;
+      size_t free_b = 0, total_b = 0;
+      CUC(cudaMemGetInfo(&free_b, &total_b));
+      size_t pool_b = forced ? ((size_t)4 << 20) : std::min<size_t>((size_t)16 << 30, free_b / 4);
+      if ((e = getenv("BUDDHA_TILE_POOL_MB"))) pool_b = (size_t)strtoull(e, nullptr, 10) << 20;
+      c->pool_entries = std::min<size_t>(pool_b / sizeof(uint32_t), 0xfffffff0u);
+      CUC(cudaMalloc(&c->d_pool, c->pool_entries * sizeof(uint32_t)));
+      CUC(cudaMalloc(&c->d_tcount, sizeof(uint32_t) * c->n_lists * 2));
+      CUC(cudaStreamCreateWithFlags(&c->apply_stream, cudaStreamNonBlocking));
+      CUC(cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->ev_applied[0], cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->ev_applied[1], cudaEventDisableTiming));
+      CUC(cudaMalloc(&c->d_tcap, sizeof(uint32_t) * c->n_lists));
+      CUC(cudaMalloc(&c->d_tbase, sizeof(unsigned long long) * c->n_lists));
+      CUC(cudaMemsetAsync(c->d_tcap, 0, sizeof(uint32_t) * c->n_lists, c->stream));
+      CUC(cudaMemsetAsync(c->d_tbase, 0, sizeof(unsigned long long) * c->n_lists, c->stream));
+      c->rp.tile_shift = c->tile_shift;
+      c->rp.n_tiles = c->n_tiles;
+      c->rp.n_warps = c->tile_warps;
+      c->rp.tcount = c->d_tcount; c->rp.tcap = c->d_tcap; c->rp.tbase = c->d_tbase;
+      c->rp.pool = c->d_pool;
+    }
+  }
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
@@ -306,6 +366,11 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters); cudaFree(c->d_max);
   cudaFree(c->spill.entries); cudaFree(c->spill.steps); cudaFree(c->spill.count);
+  if (c->apply_stream) { cudaStreamSynchronize(c->apply_stream); cudaStreamDestroy(c->apply_stream); }
+  if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
+  if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
+  if (c->ev_applied[1]) cudaEventDestroy(c->ev_applied[1]);
+  cudaFree(c->d_pool); cudaFree(c->d_tcount); cudaFree(c->d_tcap); cudaFree(c->d_tbase);
   cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -345,9 +410,8 @@ int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
   return BUDDHA_OK;
 }
 
-static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
-  if (count == 0) return BUDDHA_OK;
-  if (first + count < first) return fail(c, BUDDHA_EINVAL, "sample range wraps around 2^64");
+// One render launch (+ the orbit drain, + the tile apply when tiling is on) for [first, first+count).
+static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   RenderParams rp = c->rp;
   rp.end = first + count;
   if (c->params.flags & BUDDHA_F_SIMPLE_KERNEL) {
@@ -358,21 +422,123 @@ static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     // the cursor starts at `first`; warps take kChunk indices at a time until it passes rp.end
     unsigned long long start = first;
     CU(c, cudaMemcpyAsync(c->d_cursor, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->spill.count, 0, sizeof(unsigned int) * 2, c->stream));
+    const int b = c->tile_buf;  // which half of the list pool this launch appends to
+    if (c->tiled) {
+      if (c->apply_pending[b]) {  // the half is free again once its previous apply has finished
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_applied[b], 0));
+        c->apply_pending[b] = false;
+      }
+      rp.tcount = c->d_tcount + (size_t)b * c->n_lists;
+      rp.pool = c->d_pool + (size_t)b * (c->pool_entries / 2);
+      CU(c, cudaMemsetAsync(rp.tcount, 0, sizeof(uint32_t) * c->n_lists, c->stream));
+    }
     uint64_t want = (count + kChunk - 1) / kChunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
-    CU(c, cudaMemsetAsync(c->spill.count, 0, sizeof(unsigned int) * 2, c->stream));
-    render_persistent_kernel<<<grid, kThreadsPerCta, 0, c->stream>>>(rp, c->d_hist, c->d_cursor,
-                                                                      c->d_counters, c->spill);
+    const size_t dyn = c->tiled ? c->tile_smem : 0;
+    render_persistent_kernel<<<grid, kThreadsPerCta, dyn, c->stream>>>(rp, c->d_hist, c->d_cursor,
+                                                                        c->d_counters, c->spill);
     CU(c, cudaGetLastError());
     // orbits the warps could not run with enough lanes: finished with grid-wide refill
-    orbit_drain_kernel<<<grid, kThreadsPerCta, 0, c->stream>>>(rp, c->d_hist, c->d_counters,
-                                                                c->spill, c->d_spill_next);
+    orbit_drain_kernel<<<grid, kThreadsPerCta, dyn, c->stream>>>(rp, c->d_hist, c->d_counters,
+                                                                  c->spill, c->d_spill_next);
     c->launches += 1;
+    if (c->tiled && c->tile_calibrated) {
+      // apply this launch's lists on the second stream while the next launch renders
+      CU(c, cudaGetLastError());
+      static const bool serial = getenv("BUDDHA_TILE_SERIAL") != nullptr;  // experiment switch
+      cudaStream_t as = serial ? c->stream : c->apply_stream;
+      CU(c, cudaEventRecord(c->ev_rendered, c->stream));
+      CU(c, cudaStreamWaitEvent(as, c->ev_rendered, 0));
+      for (int t = 0; t < c->n_tiles; t++)
+        apply_tile_kernel<<<grid, kThreadsPerCta, 0, as>>>(
+            c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift);
+      CU(c, cudaEventRecord(c->ev_applied[b], as));
+      c->apply_pending[b] = true;
+      c->tile_buf = b ^ 1;
+      c->launches += c->n_tiles;
+    }
   }
   CU(c, cudaGetLastError());
   c->candidates += count;
   c->launches += 1;
+  return BUDDHA_OK;
+}
+
+// Tiling needs to know how the orbit points spread over the tiles before it can split the pool
+// into lists: the first (up to) 2^22 samples of the first render call run with all capacities at
+// zero -- every increment takes the direct reduction, the list counters still count -- and the
+// observed shares size the lists (85 % by share, 15 % spread evenly).  Happens once per context.
+static int calibrate_tiles(buddha_ctx *c, uint64_t first, uint64_t count) {
+  int rc = launch_render(c, first, count);
+  if (rc) return rc;
+  std::vector<uint32_t> cnt(c->n_lists);
+  CU(c, cudaMemcpyAsync(cnt.data(), c->d_tcount, sizeof(uint32_t) * c->n_lists,
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  // share of every tile (the warps take samples from one shared cursor, so within a tile the
+  // lists fill evenly and get equal capacity)
+  std::vector<double> tile_pts(c->n_tiles, 0.0);
+  double total = 0;
+  for (int t = 0; t < c->n_tiles; t++) {
+    for (uint32_t w = 0; w < c->tile_warps; w++) tile_pts[t] += cnt[(size_t)t * c->tile_warps + w];
+    total += tile_pts[t];
+  }
+  std::vector<uint32_t> cap(c->n_lists);
+  std::vector<unsigned long long> base(c->n_lists);
+  unsigned long long pos = 0;
+  for (int t = 0; t < c->n_tiles; t++) {
+    double share = total > 0 ? tile_pts[t] / total : 1.0 / c->n_tiles;
+    double want = (double)(c->pool_entries / 2) * (0.85 * share + 0.15 / c->n_tiles) / c->tile_warps;
+    uint32_t each = (uint32_t)std::min(want, 4294967040.0);
+    for (uint32_t w = 0; w < c->tile_warps; w++) {
+      cap[(size_t)t * c->tile_warps + w] = each;
+      base[(size_t)t * c->tile_warps + w] = pos;
+      pos += each;
+    }
+  }
+  CU(c, cudaMemcpyAsync(c->d_tcap, cap.data(), sizeof(uint32_t) * c->n_lists,
+                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_tbase, base.data(), sizeof(unsigned long long) * c->n_lists,
+                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->tile_pts_per_sample = total / (double)count;
+  c->tile_calibrated = true;
+  return BUDDHA_OK;
+}
+
+static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
+  if (count == 0) return BUDDHA_OK;
+  if (first + count < first) return fail(c, BUDDHA_EINVAL, "sample range wraps around 2^64");
+  if (!c->tiled) return launch_render(c, first, count);
+  if (!c->tile_calibrated) {
+    uint64_t n0 = std::min<uint64_t>(count, (uint64_t)1 << 22);
+    int rc = calibrate_tiles(c, first, n0);
+    if (rc) return rc;
+    first += n0;
+    count -= n0;
+  }
+  // launches sized so that the expected number of increments fills ~70 % of one pool half, and
+  // at most 2^30 samples so that a large call becomes a pipeline of render / apply pairs
+  double per = 0.7 * (double)(c->pool_entries / 2) / std::max(c->tile_pts_per_sample, 1e-6);
+  double max_launch = 1073741824.0;
+  if (const char *e = getenv("BUDDHA_TILE_LAUNCH_LOG2")) max_launch = ldexp(1.0, atoi(e));
+  uint64_t max_n = (uint64_t)std::min(std::max(per, 65536.0), max_launch);
+  max_n = std::max<uint64_t>(max_n / kChunk * kChunk, kChunk);
+  while (count > 0) {
+    uint64_t n = std::min(count, max_n);
+    int rc = launch_render(c, first, n);
+    if (rc) return rc;
+    first += n;
+    count -= n;
+  }
+  for (int b = 0; b < 2; b++) {  // everything after this call on the main stream sees the result
+    if (c->apply_pending[b]) {
+      CU(c, cudaStreamWaitEvent(c->stream, c->ev_applied[b], 0));
+      c->apply_pending[b] = false;
+    }
+  }
   return BUDDHA_OK;
 }
 

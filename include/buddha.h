@@ -38,6 +38,7 @@ enum {
 #define BUDDHA_F_NO_SHORTCUT   (1u << 0) /* disable the exact periodicity shortcut (same output)   */
 #define BUDDHA_F_SIMPLE_KERNEL (1u << 1) /* one-sample-per-thread debug kernel, reference dataflow */
 #define BUDDHA_F_EXACT_BINNING (1u << 2) /* always bin with IEEE divisions (same output)           */
+#define BUDDHA_F_FORCE_TILED   (1u << 3) /* tile-binned scatter even for small histograms (tests)  */
 
 /* Canvas + iteration limits: FractalDimensions (cudabrot.cu:46-58) and IterationControl (:62-67),
  * plus what the reference hard-codes (seed, :37) or keeps in its global struct (device, :72). */

@@ -66,6 +66,23 @@ def test_kernel_variants_agree(buddha, oracle, flags_name):
         assert_same(hist, cnt, ohist, ocnt)
 
 
+@pytest.mark.parametrize("pool_mb", [None, "1"])
+def test_tile_binned_scatter_agrees(buddha, oracle, monkeypatch, pool_mb):
+    """The tile-binned scatter used for histograms far beyond L2 (forced here on small canvases:
+    16 KB tiles, a 4 MB or 1 MB list pool so that lists overflow into the direct path) changes
+    nothing, across the calibration launch, several render calls and list overflow."""
+    if pool_mb:
+        monkeypatch.setenv("BUDDHA_TILE_POOL_MB", pool_mb)
+    for (w, h, m, c, canvas, n) in [(700, 500, 300, 10, FULL, (1 << 22) + 12345),
+                                    (900, 300, 1000, 20, (0.0, 1.0, 0.0, 0.5), 1 << 21)]:
+        ohist, ocnt, _ = oracle.render(w, h, m, c, 1337, 0, n, canvas=canvas)
+        with buddha.Renderer(w, h, m, c, canvas=canvas, flags=buddha.F_FORCE_TILED) as r:
+            r.render_samples(0, 1000)                 # shorter than the calibration window
+            r.render_samples(1000, (1 << 20) - 1000)
+            r.render_samples(1 << 20, n - (1 << 20))
+            assert_same(r.read_histogram(), r.counters(), ohist, ocnt)
+
+
 def test_shortcut_statistics(buddha):
     with buddha.Renderer(256, 256, 20000, 10000) as r:
         r.render_samples(0, 1 << 22)

@@ -2,7 +2,7 @@
 # Runs bench.py on every BASELINE.json workload (1 GPU, short) and collects the JSON lines.
 mkdir -p gpurun_out
 : > gpurun_out/workloads.jsonl
-for wl in cfg1 cfg2 cfg3 cfg3_m20000 cfg4 cfg5a cfg5b cfg5c; do
+for wl in ${WLS:-cfg1 cfg2 cfg3 cfg3_m20000 cfg4 cfg5a cfg5b cfg5c}; do
   timeout -s KILL 300 python bench.py --workload $wl --steps 2 --warmup 1 --skip-baselines \
     --samples-per-step ${1:-4294967296} >> gpurun_out/workloads.jsonl 2>> gpurun_out/workloads.err
 done
