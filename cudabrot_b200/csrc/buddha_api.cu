@@ -51,6 +51,7 @@ struct buddha_ctx {
   int tile_shift, n_tiles;
   uint32_t tile_warps;            // warps of the full grid = lists per tile
   size_t n_lists, tile_smem;
+  size_t render_smem, smem_pad;      // dynamic shared memory of the render kernel (stacks [+ tile counters])
   uint32_t *d_tcount, *d_tcap, *d_pool;   // d_tcount / d_pool hold two buffers each
   cudaStream_t apply_stream;              // apply_tiles_kernel of launch k overlaps render k+1
   cudaEvent_t ev_rendered, ev_applied[2];
@@ -270,8 +271,15 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   fill_render_params(c);
 
   int per_sm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel,
-                                                                 kThreadsPerCta, 0);
+  // the work stacks are dynamic shared memory (110 KB per CTA: opt-in above 48 KB)
+  c->render_smem = kQueueBytes;
+  if (const char *e = getenv("BUDDHA_PAD_SMEM")) c->smem_pad = (size_t)atoi(e);  // occupancy experiments
+  cudaError_t st = cudaFuncSetAttribute(render_persistent_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(kQueueBytes + c->smem_pad + 8192));
+  if (st == cudaSuccess)
+    st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel,
+                                                       kThreadsPerCta, c->render_smem + c->smem_pad);
   if (st != cudaSuccess || per_sm < 1) {
     free(c);
     return fail(nullptr, BUDDHA_ECUDA, "render kernel not launchable on device %d: %s", p->device,
@@ -328,7 +336,8 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       // the per-warp append counters are dynamic shared memory: keep the grid one resident wave
       int per_sm_tiled = 0;
       CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tiled, render_persistent_kernel,
-                                                        kThreadsPerCta, c->tile_smem));
+                                                        kThreadsPerCta,
+                                                        c->render_smem + c->smem_pad + c->tile_smem));
       if (per_sm_tiled >= 1) c->grid = per_sm_tiled * c->sm_count;
       c->tile_warps = (uint32_t)c->grid * kWarpsPerCta;
       c->n_lists = (size_t)c->n_tiles * c->tile_warps;
@@ -437,8 +446,8 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
     const size_t dyn = c->tiled ? c->tile_smem : 0;
-    render_persistent_kernel<<<grid, kThreadsPerCta, dyn, c->stream>>>(rp, c->d_hist, c->d_cursor,
-                                                                        c->d_counters, c->spill);
+    render_persistent_kernel<<<grid, kThreadsPerCta, c->render_smem + c->smem_pad + dyn, c->stream>>>(
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill);
     CU(c, cudaGetLastError());
     // orbits the warps could not run with enough lanes: finished with grid-wide refill
     orbit_drain_kernel<<<grid, kThreadsPerCta, dyn, c->stream>>>(rp, c->d_hist, c->d_counters,

@@ -22,15 +22,17 @@
 
 namespace buddha {
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 11;                // 2 CTAs x 11 warps x 10 KB of stacks fill one SM
+constexpr int kCtasPerSm = 2;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-constexpr int kStackCap = 64;                  // entries per work stack (4 stacks per warp)
+constexpr int kStackCap = 64;                  // entries per work stack (5 stacks per warp)
 constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
-constexpr int kShortIters = 33;                // escape tests longer than this go to the deep list
-constexpr int kShortBlock = 4;                 // per-step-tested steps per short round (33 = 1 + 8*4)
-constexpr int kBlock = 16;                     // unchecked steps per deep round
-constexpr int kShortExit = 24;                 // leave a phase when fewer lanes than this are busy
-constexpr int kDeepExit = 24;
+constexpr int kGenSteps = 2;                   // escape-test steps done by the sampler itself
+constexpr int kT1End = 6;                      // tier 1 covers steps kGenSteps+1 .. kT1End
+constexpr int kT2End = 14;                     // tier 2 covers steps kT1End+1 .. kT2End
+constexpr int kLateSteps = 16;                 // per-step-tested steps per `late` batch
+constexpr int kBlock = 16;                     // unchecked steps per deep round (= kLateSteps)
+constexpr int kDeepExit = 24;                  // leave a phase when fewer lanes than this are busy
 constexpr int kOrbExit = 16;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -294,99 +296,97 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 
 // ---- the persistent renderer ----------------------------------------------------------------
 //
-// One warp is the unit of scheduling.  It owns four stacks in shared memory and moves through
-// five phases, always choosing one that can keep (nearly) all 32 lanes busy:
+// One warp is the unit of scheduling.  It owns five stacks in shared memory and moves through
+// six phases.  The escape test of a fresh candidate is a chain of fixed-length, straight-line
+// TIERS: all 32 lanes run the same number of steps with the exact per-step test and no per-lane
+// refill, survivors are ballot-compacted onto the next stack.  The survival curve is so flat
+// (33 % survive step 1, 19 % step 2, 9.8 % step 6, 3.1 % step 14, 1.8 % step 30) that a tier
+// keeps 65..78 % of its lane-steps useful, while the bookkeeping per step drops to one predicated
+// add and one predicate update.
 //
-//   gen     draw 32 candidates (Philox), cardioid/bulb test, FIRST iteration + escape test, all in
-//           straight-line code at full lane utilisation (2/3 of all candidates escape right here);
-//           survivors are ballot-compacted onto the `short` stack.
-//   short   iterations 2..kShortIters with the exact per-step escape test, kShortBlock steps per
-//           round, per-lane refill from the `short` stack.  Escapes are classified here; samples
-//           that reach kShortIters move to the `deep` stack.
+//   gen     draw 32 candidates (Philox), cardioid/bulb test, steps 1..2      -> t1 (c only)
+//   tier 1  steps 3..6  (re-computes steps 1..2 from c: 8 FP64, saves 16 B)  -> t2 (c only)
+//   tier 2  steps 7..14 (re-computes steps 1..6)                             -> late
+//   late    16 per-step-tested steps from a stored state (c, z, it): tier-2 survivors, samples
+//           handed back by deep, tails that have fewer than kBlock steps left -> deep / late
 //   deep    long escape tests: kBlock unchecked steps (4 FP64 instr each) per round, one |z|^2
-//           test per round, exact periodicity shortcut.  A lane whose round ended outside the
-//           radius-2 disc is handed to the `replay` stack with its round-start state.
-//   replay  same code as short, fed from the `replay` stack: finds the exact escape index of the
-//           handed-back samples with the per-step test; also continues suspended short lanes.
+//           test per round, exact periodicity shortcut, per-lane refill.  A lane whose round
+//           ended outside the radius-2 disc is handed to `late` with its round-start state.
 //   orbit   re-iterate accepted samples for exactly i+1 steps and scatter with red.global.add.
 //
-// Pushes: gen->{short,orbit}, short->{deep,orbit,replay}, deep->{replay}, replay->{orbit,deep}.
-// The scheduler serves the stacks in the order orbit, replay, deep, short, gen; a phase starts a
-// round only while each stack it MUST push to holds < 32 entries (replay only feeds deep while
-// deep has room, otherwise its lanes keep stepping), so with 64-entry stacks nothing can overflow
-// and some phase can always run.
+// Every tier may also push accepted escapes to `orbit`.  The scheduler serves the stacks in the
+// order orbit, late, deep, t2, t1, gen; a phase runs only while each stack it pushes to holds
+// < 32 entries (late re-queues its own survivors while deep is full), so the 64-entry stacks
+// cannot overflow and some phase can always run.
+//
+// Lanes that have escaped keep stepping until their tier ends; their values grow to inf/NaN,
+// which no later code reads (the `alive` predicate is sticky and NaN compares false).
 
-template <int CAP>
-struct Stack {
-  double cx[CAP], cy[CAP], x[CAP], y[CAP];
-  int it[CAP];  // iterations done (orbit stack: steps still to record)
+struct CStack {  // candidates that re-compute their state from c
+  double2 c[kStackCap];
 };
 
-// `short` holds fresh candidates only (z after the first step is recomputed from c at the pop:
-// 4 FP64 instructions instead of 20 B of shared memory per entry); a short lane that has to be
-// suspended goes to `replay`, which keeps the full state.
-struct ShortStack {
-  double cx[kStackCap], cy[kStackCap];
+struct ZStack {  // late: it = iterations done; orbit: it = steps still to record
+  double2 c[kStackCap], z[kStackCap];
+  int it[kStackCap];
 };
 
 // `deep` entries carry their Brent checkpoint, so suspending a lane does not restart the
 // periodicity search (long cycles need long uninterrupted windows).
 struct DeepStack {
-  double cx[kStackCap], cy[kStackCap], x[kStackCap], y[kStackCap], rx[kStackCap], ry[kStackCap];
-  int it[kStackCap];
-  unsigned age[kStackCap];
+  double2 c[kStackCap], z[kStackCap], r[kStackCap];
+  uint2 meta[kStackCap];  // (iterations done, age)
 };
 
 struct WarpQueues {
-  ShortStack shrt;
   DeepStack deep;
-  Stack<kStackCap> rply, orb;
-  int rply_stay[kStackCap];
+  ZStack late, orb;
+  CStack t1, t2;
 };
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
-  int short_n, deep_n, rply_n, orb_n;      // stack heights (warp-uniform)
-  unsigned long long chunk_next, chunk_end; // sample indices still owned by this warp
+  int t1_n, t2_n, late_n, deep_n, orb_n;  // stack heights (warp-uniform)
+  unsigned long long chunk_base;           // first sample index of the chunk this warp owns
+  uint32_t chunk_off, chunk_len;           // progress inside the chunk
   bool exhausted;                          // the global cursor ran past p.end
   // per-lane event counters, flushed to global memory at every cursor grab
   uint32_t n_rej, n_hit, n_acc, n_cyc, n_exact;
-  uint32_t e_ref, e_exec, p_pts, p_inc;
+  uint32_t steps;      // iterations that advanced a sample (count for escape_iters AND executed)
+  uint32_t skipped;    // iterations the periodicity shortcut did not have to run (escape_iters only)
+  uint32_t wasted;     // deep rounds that were rolled back (executed only)
+  uint32_t p_pts, p_inc;
 };
 
 __device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
-  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, 0u, ws.n_acc, ws.e_ref, ws.p_pts,
-                           ws.p_inc, ws.e_exec, ws.n_cyc, ws.n_exact};
+  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, 0u, ws.n_acc, ws.steps, ws.p_pts,
+                           ws.p_inc, ws.steps, ws.n_cyc, ws.n_exact};
 #pragma unroll
   for (int k = 0; k < kCntSlots; k++) {
     if (k == kCntTooEarly) continue;  // derived on the host: candidates - the other classes
     unsigned long long x = v[k];
+    if (k == kCntEscapeIters) x += ws.skipped;
+    if (k == kCntExecuted) x += ws.wasted;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
     if (lane_id() == 0 && x) atomicAdd(counters + k, x);
   }
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 }
 
-// Push one entry per lane with `pred` set (ballot compaction); returns the slot where pred.
-template <int CAP>
-__device__ __forceinline__ int stack_push(Stack<CAP> &st, int &height, bool pred, double cx,
-                                          double cy, double x, double y, int it) {
+// Ballot-compacted push of one entry per lane with `pred` set.
+__device__ __forceinline__ int push_slot(int &height, bool pred) {
   unsigned m = __ballot_sync(kFull, pred);
   int slot = height + __popc(m & lanemask_lt());
   height += __popc(m);
-  if (pred) { st.cx[slot] = cx; st.cy[slot] = cy; st.x[slot] = x; st.y[slot] = y; st.it[slot] = it; }
   return slot;
 }
 
-// Pop one entry for every lane with `want` set while entries last; returns the slot or -1.
-__device__ __forceinline__ int stack_pop(bool want, int &height) {
-  unsigned m = __ballot_sync(kFull, want);
-  int rank = __popc(m & lanemask_lt());
-  int slot = (want && rank < height) ? (height - 1 - rank) : -1;
-  height -= min(__popc(m), height);
-  return slot;
+__device__ __forceinline__ void push_z(ZStack &st, int &height, bool pred, double cx, double cy,
+                                       double x, double y, int it) {
+  int slot = push_slot(height, pred);
+  if (pred) { st.c[slot] = make_double2(cx, cy); st.z[slot] = make_double2(x, y); st.it[slot] = it; }
 }
 
 __device__ __forceinline__ void push_orbit(WarpQueues &q, WarpState &ws, bool acc, double cx,
@@ -394,53 +394,68 @@ __device__ __forceinline__ void push_orbit(WarpQueues &q, WarpState &ws, bool ac
   if (__ballot_sync(kFull, acc) == 0u) return;
   ws.n_acc += acc ? 1u : 0u;
   ws.p_pts += acc ? (uint32_t)n : 0u;
-  stack_push(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
+  push_z(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
 }
 
-// (a) sampler + first iteration.  One batch = one candidate per lane.
+// N steps with the exact per-step escape test (cudabrot.cu:331-338) for all lanes at once.
+// *cnt = steps a lane ran while it had not escaped (the escaping step included); `alive` on
+// return: never escaped.  A step limit below N is applied by the caller afterwards.
+template <int N>
+__device__ __forceinline__ void tested_steps(double &x, double &y, double cx, double cy,
+                                             bool &alive, int &cnt) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    const bool e = norm4(x, y) > 16.0;
+    cnt += alive ? 1 : 0;
+    alive = alive && !e;
+  }
+}
+
+// (a) sampler + steps 1..kGenSteps.  One batch = one candidate per lane.
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
                                           unsigned long long *counters) {
   const unsigned lane = lane_id();
+  const int allowed = max(0, min(kGenSteps, p.max_it));  // IterateMandelbrot stops at max
+  const bool last = p.max_it <= kGenSteps;               // survivors have run all max iterations
+  const bool may_accept = kGenSteps - 1 >= p.min_it;
 #pragma unroll 1
-  while (ws.short_n < 32 && ws.orb_n < 32) {
-    if (ws.chunk_next >= ws.chunk_end) {
+  while (ws.t1_n < 32 && ws.orb_n < 32) {
+    if (ws.chunk_off >= ws.chunk_len) {
       if (ws.exhausted) break;
       flush_counters(ws, counters);
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
       base = __shfl_sync(kFull, base, 0);
       if (base >= p.end) { ws.exhausted = true; break; }
-      ws.chunk_next = base;
-      ws.chunk_end = (base + kChunk < p.end) ? base + kChunk : p.end;
+      ws.chunk_base = base;
+      ws.chunk_off = 0;
+      ws.chunk_len = (base + kChunk <= p.end) ? (uint32_t)kChunk : (uint32_t)(p.end - base);
     }
-    unsigned long long s = ws.chunk_next + lane;
-    bool valid = s < ws.chunk_end;
-    ws.chunk_next = (ws.chunk_next + 32 < ws.chunk_end) ? ws.chunk_next + 32 : ws.chunk_end;
-    uint4 r = philox4x32_10(s, p);
-    double cx = coord2_from_words(r.x, r.y);
-    double cy = coord2_from_words(r.z, r.w);
-    bool rej = rejected2(cx, cy);
-    bool alive = valid && !rej;
+    const uint32_t o = ws.chunk_off + lane;
+    const bool valid = o < ws.chunk_len;
+    ws.chunk_off += 32;
+    uint4 r = philox4x32_10(ws.chunk_base + o, p);
+    const double cx = coord2_from_words(r.x, r.y);
+    const double cy = coord2_from_words(r.z, r.w);
+    const bool rej = rejected2(cx, cy);
+    const bool cand = valid && !rej;
     ws.n_rej += (valid && rej) ? 1u : 0u;
-    if (p.max_it <= 0) {  // IterateMandelbrot returns max at once (cudabrot.cu:326,339,407)
-      ws.n_hit += alive ? 1u : 0u;
-      continue;
-    }
     double x = cx, y = cy;
-    BUDDHA_ZSTEP(x, y, cx, cy);
-    bool esc = norm4(x, y) > 16.0;
-    ws.e_exec += alive ? 1u : 0u;
-    ws.e_ref += (alive && (esc || p.max_it == 1)) ? 1u : 0u;
-    ws.n_hit += (alive && !esc && p.max_it == 1) ? 1u : 0u;
-    push_orbit(q, ws, alive && esc && (0 >= p.min_it), cx, cy, 1);
-    {
-      const bool keep = alive && !esc && p.max_it > 1;
-      unsigned m = __ballot_sync(kFull, keep);
-      int slot = ws.short_n + __popc(m & lanemask_lt());
-      ws.short_n += __popc(m);
-      if (keep) { q.shrt.cx[slot] = cx; q.shrt.cy[slot] = cy; }
+    bool alive = cand;
+    int cnt = 0;
+    tested_steps<kGenSteps>(x, y, cx, cy, alive, cnt);
+    const bool esc = cand && !alive && cnt <= allowed;
+    ws.steps += (uint32_t)min(cnt, allowed);
+    const bool surv = cand && !esc;
+    if (last) {
+      ws.n_hit += surv ? 1u : 0u;
+    } else {
+      int slot = push_slot(ws.t1_n, surv);
+      if (surv) q.t1.c[slot] = make_double2(cx, cy);
     }
+    if (may_accept) push_orbit(q, ws, esc && (cnt - 1 >= p.min_it), cx, cy, cnt);
   }
   __syncwarp();
 }
@@ -453,82 +468,78 @@ __device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pre
   int slot = ws.deep_n + __popc(m & lanemask_lt());
   ws.deep_n += __popc(m);
   if (pred) {
-    q.deep.cx[slot] = cx; q.deep.cy[slot] = cy; q.deep.x[slot] = x; q.deep.y[slot] = y;
-    q.deep.rx[slot] = rx; q.deep.ry[slot] = ry; q.deep.it[slot] = it; q.deep.age[slot] = age;
+    q.deep.c[slot] = make_double2(cx, cy); q.deep.z[slot] = make_double2(x, y);
+    q.deep.r[slot] = make_double2(rx, ry); q.deep.meta[slot] = make_uint2((unsigned)it, age);
   }
 }
 
-// (b) escape test with the per-step test and per-lane refill.  kReplay = false: fresh candidates
-// from the `short` stack (iterations 2..kShortIters, then on to `deep`).  kReplay = true: the
-// `replay` stack (samples handed back by deep, which run here until they escape or reach max,
-// and suspended short lanes).
-template <bool kReplay>
-__device__ __forceinline__ void short_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                            bool drain) {
-  int &src_n = kReplay ? ws.rply_n : ws.short_n;
-  bool act = false;
-  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
-  int it = 0, stay = 0;
-#pragma unroll 1
-  for (;;) {
-    // keep room for 32 pushes per target; replay may run with deep full (its lanes then wait)
-    if (ws.orb_n >= 32 || (!kReplay && ws.deep_n >= 32)) break;
-    const bool deep_room = ws.deep_n < 32;
-    if (src_n > 0 && __ballot_sync(kFull, !act)) {
-      int slot = stack_pop(!act, src_n);
-      if (slot >= 0) {
-        if (kReplay) {
-          cx = q.rply.cx[slot]; cy = q.rply.cy[slot]; x = q.rply.x[slot]; y = q.rply.y[slot];
-          it = q.rply.it[slot]; stay = q.rply_stay[slot];
-        } else {
-          cx = q.shrt.cx[slot]; cy = q.shrt.cy[slot];
-          x = cx; y = cy;
-          BUDDHA_ZSTEP(x, y, cx, cy);  // the first step again (gen did not keep z1)
-          it = 1; stay = kShortIters;
-        }
-        act = true;
-      }
-      __syncwarp();
-    }
-    unsigned am = __ballot_sync(kFull, act);
-    if (am == 0u) break;
-    if (!drain && __popc(am) < kShortExit) break;
-
-    // kShortBlock steps; `alive` lanes are still before their escape / limit
-    const int allowed = min(kShortBlock, p.max_it - it);
-    bool alive = act, escd = false;
-    int cnt = 0;
+// (b) one tier of the escape test: pops up to 32 candidates that survived A steps, re-computes
+// those steps from c (no tests needed: they are known not to escape), runs steps A+1..A+N with the
+// per-step test.  kToLate = false: survivors go to t2 as c only; true: to `late` with their state.
+template <int A, int N, bool kToLate>
+__device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                           CStack &src, int &src_n) {
+  const int take = min(src_n, 32);
+  const bool act = (int)lane_id() < take;
+  src_n -= take;
+  double2 c = make_double2(0.0, 0.0);
+  if (act) c = src.c[src_n + (int)lane_id()];
+  const double cx = c.x, cy = c.y;
+  double x = cx, y = cy;
 #pragma unroll
-    for (int k = 0; k < kShortBlock; k++) {
-      BUDDHA_ZSTEP(x, y, cx, cy);
-      bool e = norm4(x, y) > 16.0;
-      cnt += alive ? 1 : 0;
-      escd = escd || (alive && e);
-      alive = alive && !e && (cnt < allowed);
-    }
-    it += cnt;
-    ws.e_exec += (uint32_t)cnt;
-    bool hit = act && !escd && it >= p.max_it;
-    bool todeep = act && !escd && !hit && it >= stay;
-    if (__ballot_sync(kFull, escd || hit || todeep)) {
-      ws.e_ref += (escd || hit) ? (uint32_t)it : 0u;  // esc: i+1 = it; hit: max = it
-      ws.n_hit += hit ? 1u : 0u;
-      push_orbit(q, ws, escd && (it - 1 >= p.min_it), cx, cy, it);
-      if (todeep && (!(norm4(cx, cy) <= 15.99) || it + kBlock > p.max_it)) {
-        // |c| too close to 2 for deep's no-re-entry argument, or no room for a full unchecked
-        // round before max: per-step test to the end
-        stay = p.max_it;
-        todeep = false;
-      }
-      todeep = todeep && deep_room;  // replay with deep full: keep stepping here, retry later
-      push_deep(q, ws, todeep, cx, cy, x, y, x, y, it, 0u);
-      if (escd || hit || todeep) { act = false; cx = cy = x = y = 0.0; it = 0; }
-    }
+  for (int k = 0; k < A; k++) BUDDHA_ZSTEP(x, y, cx, cy);
+  bool alive = act;
+  int cnt = 0;
+  tested_steps<N>(x, y, cx, cy, alive, cnt);
+  const int allowed = min(N, p.max_it - A);  // >= 1: nothing is pushed here once max is reached
+  const bool esc = act && !alive && cnt <= allowed;
+  ws.steps += (uint32_t)min(cnt, allowed);
+  const bool surv = act && !esc;
+  if (p.max_it <= A + N) {
+    ws.n_hit += surv ? 1u : 0u;
+  } else if (kToLate) {
+    push_z(q.late, ws.late_n, surv, cx, cy, x, y, A + N);
+  } else {
+    int slot = push_slot(ws.t2_n, surv);
+    if (surv) q.t2.c[slot] = make_double2(cx, cy);
   }
-  // suspend: lanes still in flight go to the replay stack with their full state
-  if (__ballot_sync(kFull, act)) {
-    int ss = stack_push(q.rply, ws.rply_n, act, cx, cy, x, y, it);
-    if (act) q.rply_stay[ss] = stay;
+  if (A + N - 1 >= p.min_it) push_orbit(q, ws, esc && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
+  __syncwarp();
+}
+
+// (b') 16 per-step-tested steps from a stored state.  Entries: tier-2 survivors (it = 14), samples
+// handed back by deep (certain to escape within kBlock steps), tails (fewer than kBlock steps left
+// below max), samples that deep cannot take (|c| too close to 2, or deep full right now).
+__device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q, WarpState &ws) {
+  const int take = min(ws.late_n, 32);
+  const bool act = (int)lane_id() < take;
+  ws.late_n -= take;
+  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
+  int it = 0;
+  if (act) {
+    const int slot = ws.late_n + (int)lane_id();
+    double2 c = q.late.c[slot], z = q.late.z[slot];
+    cx = c.x; cy = c.y; x = z.x; y = z.y; it = q.late.it[slot];
+  }
+  __syncwarp();  // the slots are re-used by the pushes below
+  const bool deep_room = ws.deep_n < 32;
+  bool alive = act;
+  int cnt = 0;
+  tested_steps<kLateSteps>(x, y, cx, cy, alive, cnt);
+  const int allowed = min(kLateSteps, p.max_it - it);  // >= 1 for every stored entry
+  const bool esc = act && !alive && cnt <= allowed;
+  ws.steps += act ? (uint32_t)min(cnt, allowed) : 0u;
+  const bool surv = act && !esc;
+  const int nit = it + kLateSteps;
+  const bool hit = surv && nit >= p.max_it;  // ran all max iterations (allowed == max - it)
+  ws.n_hit += hit ? 1u : 0u;
+  push_orbit(q, ws, esc && (it + cnt - 1 >= p.min_it), cx, cy, it + cnt);
+  const bool cont = surv && !hit;
+  if (__ballot_sync(kFull, cont)) {
+    // deep's no-re-entry argument needs |c| <= 1.99937, and a full unchecked round must fit
+    const bool todeep = cont && deep_room && norm4(cx, cy) <= 15.99 && nit + kBlock <= p.max_it;
+    push_deep(q, ws, todeep, cx, cy, x, y, x, y, nit, 0u);
+    push_z(q.late, ws.late_n, cont && !todeep, cx, cy, x, y, nit);
   }
   __syncwarp();
 }
@@ -549,16 +560,20 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
   unsigned last = 0;    // the age after which no further full round fits below max_it
 #pragma unroll 1
   for (;;) {
-    if (ws.rply_n >= 32) break;  // keep room for 32 hand-backs
+    if (ws.late_n >= 32) break;  // keep room for 32 hand-backs
     if (ws.deep_n > 0 && __ballot_sync(kFull, !act)) {
-      int slot = stack_pop(!act, ws.deep_n);
-      if (slot >= 0) {
-        cx = q.deep.cx[slot]; cy = q.deep.cy[slot];
-        x = q.deep.x[slot]; y = q.deep.y[slot]; it0 = q.deep.it[slot];
-        rx = q.deep.rx[slot]; ry = q.deep.ry[slot]; age0 = age = q.deep.age[slot];
+      unsigned m = __ballot_sync(kFull, !act);
+      int rank = __popc(m & lanemask_lt());
+      if (!act && rank < ws.deep_n) {
+        const int slot = ws.deep_n - 1 - rank;
+        double2 c = q.deep.c[slot], z = q.deep.z[slot], r = q.deep.r[slot];
+        uint2 meta = q.deep.meta[slot];
+        cx = c.x; cy = c.y; x = z.x; y = z.y; rx = r.x; ry = r.y;
+        it0 = (int)meta.x; age0 = age = meta.y;
         last = age0 + (unsigned)(max_it - it0) / kBlock;  // >= age0 + 1 (it0 + kBlock <= max)
         act = true;
       }
+      ws.deep_n -= min(__popc(m), ws.deep_n);
       __syncwarp();
     }
     unsigned am = __ballot_sync(kFull, act);
@@ -590,21 +605,18 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       if (fin && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
       const bool hit = fin && !out && (cyc || it >= max_it);  // periodic, or ran all max iterations
       const bool back = fin && !hit;                    // escaped in the round, or a short tail
-      ws.e_exec += fin ? (uint32_t)(it - it0) + (out ? (uint32_t)kBlock : 0u) : 0u;
+      ws.steps += fin ? (uint32_t)(it - it0) : 0u;
+      ws.wasted += (fin && out) ? (uint32_t)kBlock : 0u;
+      ws.skipped += hit ? (uint32_t)(max_it - it) : 0u;
       ws.n_hit += hit ? 1u : 0u;
       ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
-      ws.e_ref += hit ? (uint32_t)max_it : 0u;
-      if (__ballot_sync(kFull, back)) {
-        int ss = stack_push(q.rply, ws.rply_n, back, cx, cy, x, y, it);
-        // an escape is certain within the next kBlock steps; a tail just runs out at max
-        if (back) q.rply_stay[ss] = out ? it + kBlock : max_it;
-      }
+      if (__ballot_sync(kFull, back)) push_z(q.late, ws.late_n, back, cx, cy, x, y, it);
       if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
     }
   }
   {
     int it = it0 + (int)((age - age0) * kBlock);
-    ws.e_exec += act ? (uint32_t)(it - it0) : 0u;
+    ws.steps += act ? (uint32_t)(it - it0) : 0u;
     push_deep(q, ws, act, cx, cy, x, y, rx, ry, it, age);  // keeps the checkpoint and its schedule
   }
   __syncwarp();
@@ -637,20 +649,22 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
 #pragma unroll 1
   for (;;) {
     if (ws.orb_n > 0 && __ballot_sync(kFull, !o.act)) {
-      int slot = stack_pop(!o.act, ws.orb_n);
-      if (slot >= 0) {
-        o.cx = q.orb.cx[slot]; o.cy = q.orb.cy[slot];
-        o.x = q.orb.x[slot]; o.y = q.orb.y[slot]; o.n = q.orb.it[slot];
+      unsigned m = __ballot_sync(kFull, !o.act);
+      int rank = __popc(m & lanemask_lt());
+      if (!o.act && rank < ws.orb_n) {
+        const int slot = ws.orb_n - 1 - rank;
+        double2 c = q.orb.c[slot], z = q.orb.z[slot];
+        o.cx = c.x; o.cy = c.y; o.x = z.x; o.y = z.y; o.n = q.orb.it[slot];
         o.act = true;
       }
+      ws.orb_n -= min(__popc(m), ws.orb_n);
       __syncwarp();
     }
     unsigned am = __ballot_sync(kFull, o.act);
     if (__popc(am) < kOrbExit) break;
     orbit_step(p, o, ws, hist);
   }
-  if (__ballot_sync(kFull, o.act))
-    stack_push(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
+  if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
 }
 
@@ -663,35 +677,41 @@ struct OrbitSpill {
   unsigned int capacity;
 };
 
-__global__ void __launch_bounds__(kThreadsPerCta)
+// Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles counters per warp.
+constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
+
+__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSm)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
                          unsigned long long *__restrict__ counters, OrbitSpill spill) {
-  __shared__ WarpQueues queues[kWarpsPerCta];
-  extern __shared__ uint32_t tile_counters[];  // n_tiles per warp when tiling is on, else empty
-  WarpQueues &q = queues[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpQueues &q = reinterpret_cast<WarpQueues *>(smem_raw)[threadIdx.x >> 5];
+  uint32_t *tile_counters = reinterpret_cast<uint32_t *>(smem_raw + kQueueBytes);
   const Sink sink = {hist, tile_counters + (threadIdx.x >> 5) * p.n_tiles,
                      blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
   tile_counters_load(p, sink, true);
   WarpState ws;
-  ws.short_n = ws.deep_n = ws.rply_n = ws.orb_n = 0;
-  ws.chunk_next = ws.chunk_end = 0;
+  ws.t1_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
+  ws.chunk_base = 0;
+  ws.chunk_off = ws.chunk_len = 0;
   ws.exhausted = false;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 
 #pragma unroll 1
   for (;;) {
     // strict priority along the push graph: a phase is reached only when every stack it pushes
     // to holds < 32 entries
     if (ws.orb_n >= 32) { orbit_phase(p, q, ws, sink); continue; }
-    if (ws.rply_n >= 32) { short_phase<true>(p, q, ws, false); continue; }
+    if (ws.late_n >= 32) { late_phase(p, q, ws); continue; }
     if (ws.deep_n >= 32) { deep_phase(p, q, ws, false); continue; }
-    if (ws.short_n >= 32) { short_phase<false>(p, q, ws, false); continue; }
-    if (!(ws.exhausted && ws.chunk_next >= ws.chunk_end)) { gen_phase(p, q, ws, cursor, counters); continue; }
-    // the sample range is used up: run the partial stacks dry
-    if (ws.rply_n > 0) { short_phase<true>(p, q, ws, true); continue; }
-    if (ws.short_n > 0) { short_phase<false>(p, q, ws, true); continue; }
+    if (ws.t2_n >= 32) { tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n); continue; }
+    if (ws.t1_n >= 32) { tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n); continue; }
+    if (!(ws.exhausted && ws.chunk_off >= ws.chunk_len)) { gen_phase(p, q, ws, cursor, counters); continue; }
+    // the sample range is used up: run the partial stacks dry, upstream first
+    if (ws.t1_n > 0) { tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n); continue; }
+    if (ws.t2_n > 0) { tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n); continue; }
+    if (ws.late_n > 0) { late_phase(p, q, ws); continue; }
     if (ws.deep_n > 0) { deep_phase(p, q, ws, true); continue; }
     break;
   }
@@ -703,7 +723,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     for (int k = lane_id(); k < ws.orb_n; k += 32) {
       unsigned dst = base + k;
       if (dst < spill.capacity) {
-        spill.entries[dst] = make_double4(q.orb.cx[k], q.orb.cy[k], q.orb.x[k], q.orb.y[k]);
+        spill.entries[dst] = make_double4(q.orb.c[k].x, q.orb.c[k].y, q.orb.z[k].x, q.orb.z[k].y);
         spill.steps[dst] = q.orb.it[k];
       }
     }
@@ -724,7 +744,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   tile_counters_load(p, sink, false);  // continue the lists where the render kernel stopped
   WarpState ws;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.e_ref = ws.e_exec = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
   OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
   bool more = true;
 #pragma unroll 1

@@ -54,6 +54,19 @@ def test_histogram_and_counters_match_oracle(buddha, oracle, name):
     assert_same(hist, cnt, ohist, ocnt)
 
 
+@pytest.mark.parametrize("m", [2, 3, 5, 6, 7, 13, 14, 15, 17, 29, 30, 31, 45, 46, 47, 62])
+def test_tier_boundaries(buddha, oracle, m):
+    """max-iter on, just below and just above every tier boundary of the escape test (2, 6, 14,
+    30, 46, ...), with cutoffs that accept escapes inside the first tiers."""
+    for c in (0, 1, 2, 5, 6, 13, 14):
+        if c >= m:
+            continue
+        n = (1 << 17) + 77
+        ohist, ocnt, _ = oracle.render(96, 64, m, c, 4242, 1 << 33, n)
+        hist, cnt = gpu_render(buddha, 96, 64, m, c, 4242, 1 << 33, n)
+        assert_same(hist, cnt, ohist, ocnt)
+
+
 @pytest.mark.parametrize("flags_name", ["F_NO_SHORTCUT", "F_SIMPLE_KERNEL", "F_EXACT_BINNING"])
 def test_kernel_variants_agree(buddha, oracle, flags_name):
     """The periodicity shortcut, the division-free binning and the persistent scheduling change
