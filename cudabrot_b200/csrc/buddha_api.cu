@@ -44,20 +44,20 @@ struct buddha_ctx {
   unsigned long long *d_cursor;   // offset handed out so far in the current launch
   unsigned long long *d_counters; // kCntSlots accumulators
   uint32_t *d_max;
-  OrbitSpill spill;               // grid-wide list of orbits left over by the render kernel
-  unsigned int *d_spill_next;
+  OrbitSpill spill[2];            // grid-wide lists of orbits left over by the render kernel
+  unsigned int *d_spill_next[2];  // (two: the drain of launch k overlaps the render of launch k+1)
   // tile-binned scatter (histograms far beyond L2), see scatter() in buddha_kernels.cuh
   bool tiled, tile_calibrated;
   int tile_shift, n_tiles;
   uint32_t tile_warps;            // warps of the full grid = lists per tile
   size_t n_lists, tile_smem;
   size_t render_smem, smem_pad;      // dynamic shared memory of the render kernel (stacks [+ tile counters])
-  uint32_t *d_tcount, *d_tcap, *d_pool;   // d_tcount / d_pool hold two buffers each
+  uint32_t *d_tcount, *d_tcap, *d_pool;   // d_tcount / d_pool hold two buffers each; d_tcap per tile
   cudaStream_t apply_stream;              // apply_tiles_kernel of launch k overlaps render k+1
   cudaEvent_t ev_rendered, ev_applied[2];
   bool apply_pending[2];
   int tile_buf;
-  unsigned long long *d_tbase;
+  uint32_t *d_tbase;              // per tile: first pool entry (inside one pool half)
   size_t pool_entries;
   double tile_pts_per_sample;
   uint16_t *d_gray;               // tone-mapped image, allocated on first use
@@ -309,11 +309,13 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCntSlots));
   CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
   CUC(cudaMalloc(&c->d_max, sizeof(uint32_t)));
-  c->spill.capacity = (unsigned)c->grid * kWarpsPerCta * kStackCap;  // every warp spills < kStackCap
-  CUC(cudaMalloc(&c->spill.entries, sizeof(double4) * c->spill.capacity));
-  CUC(cudaMalloc(&c->spill.steps, sizeof(int) * c->spill.capacity));
-  CUC(cudaMalloc(&c->spill.count, sizeof(unsigned int) * 2));
-  c->d_spill_next = c->spill.count + 1;
+  for (int b = 0; b < 2; b++) {
+    c->spill[b].capacity = (unsigned)c->grid * kWarpsPerCta * kStackCap;  // every warp spills < kStackCap
+    CUC(cudaMalloc(&c->spill[b].entries, sizeof(double4) * c->spill[b].capacity));
+    CUC(cudaMalloc(&c->spill[b].steps, sizeof(int) * c->spill[b].capacity));
+    CUC(cudaMalloc(&c->spill[b].count, sizeof(unsigned int) * 2));
+    c->d_spill_next[b] = c->spill[b].count + 1;
+  }
   CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
   {
     // tile-binned scatter: on for histograms >= 768 MB (config 3: 1.6 GB), or when forced (tests)
@@ -328,8 +330,8 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       if ((e = getenv("BUDDHA_TILE_SHIFT"))) c->tile_shift = atoi(e);
       if (c->tile_shift < 8 || c->tile_shift > 28) c->tile_shift = 24;
       c->n_tiles = (int)((c->cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
-      c->tile_smem = (size_t)c->n_tiles * kWarpsPerCta * sizeof(uint32_t);
-      if (c->tile_smem > 8192) {  // > 512 tiles: not a case tiling is meant for
+      c->tile_smem = (size_t)c->n_tiles * kWarpsPerCta * sizeof(uint2);
+      if (c->n_tiles > 512) {  // not a case tiling is meant for
         buddha_destroy(c);
         return fail(nullptr, BUDDHA_EINVAL, "tile-binned scatter supports at most 512 tiles");
       }
@@ -345,21 +347,26 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       CUC(cudaMemGetInfo(&free_b, &total_b));
       size_t pool_b = forced ? ((size_t)4 << 20) : std::min<size_t>((size_t)16 << 30, free_b / 4);
       if ((e = getenv("BUDDHA_TILE_POOL_MB"))) pool_b = (size_t)strtoull(e, nullptr, 10) << 20;
-      c->pool_entries = std::min<size_t>(pool_b / sizeof(uint32_t), 0xfffffff0u);
+      c->pool_entries = std::min<size_t>(pool_b / sizeof(uint32_t), 0xfffffff0u);  // 32-bit slots
       CUC(cudaMalloc(&c->d_pool, c->pool_entries * sizeof(uint32_t)));
       CUC(cudaMalloc(&c->d_tcount, sizeof(uint32_t) * c->n_lists * 2));
-      CUC(cudaStreamCreateWithFlags(&c->apply_stream, cudaStreamNonBlocking));
+      {
+        // high priority: apply CTAs slip into the space the resident render CTAs leave free
+        int prio_lo = 0, prio_hi = 0;
+        CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUC(cudaStreamCreateWithPriority(&c->apply_stream, cudaStreamNonBlocking, prio_hi));
+      }
       CUC(cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->ev_applied[0], cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->ev_applied[1], cudaEventDisableTiming));
-      CUC(cudaMalloc(&c->d_tcap, sizeof(uint32_t) * c->n_lists));
-      CUC(cudaMalloc(&c->d_tbase, sizeof(unsigned long long) * c->n_lists));
-      CUC(cudaMemsetAsync(c->d_tcap, 0, sizeof(uint32_t) * c->n_lists, c->stream));
-      CUC(cudaMemsetAsync(c->d_tbase, 0, sizeof(unsigned long long) * c->n_lists, c->stream));
+      CUC(cudaMalloc(&c->d_tcap, sizeof(uint32_t) * c->n_tiles));
+      CUC(cudaMalloc(&c->d_tbase, sizeof(uint32_t) * c->n_tiles));
+      CUC(cudaMemsetAsync(c->d_tcap, 0, sizeof(uint32_t) * c->n_tiles, c->stream));
+      CUC(cudaMemsetAsync(c->d_tbase, 0, sizeof(uint32_t) * c->n_tiles, c->stream));
       c->rp.tile_shift = c->tile_shift;
       c->rp.n_tiles = c->n_tiles;
       c->rp.n_warps = c->tile_warps;
-      c->rp.tcount = c->d_tcount; c->rp.tcap = c->d_tcap; c->rp.tbase = c->d_tbase;
+      c->rp.tcount = c->d_tcount; c->rp.tile_cap = c->d_tcap; c->rp.tile_base = c->d_tbase;
       c->rp.pool = c->d_pool;
     }
   }
@@ -374,7 +381,9 @@ void buddha_destroy(buddha_ctx *c) {
   cudaSetDevice(c->params.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters); cudaFree(c->d_max);
-  cudaFree(c->spill.entries); cudaFree(c->spill.steps); cudaFree(c->spill.count);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->spill[b].entries); cudaFree(c->spill[b].steps); cudaFree(c->spill[b].count);
+  }
   if (c->apply_stream) { cudaStreamSynchronize(c->apply_stream); cudaStreamDestroy(c->apply_stream); }
   if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
   if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
@@ -431,8 +440,8 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     // the cursor starts at `first`; warps take kChunk indices at a time until it passes rp.end
     unsigned long long start = first;
     CU(c, cudaMemcpyAsync(c->d_cursor, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemsetAsync(c->spill.count, 0, sizeof(unsigned int) * 2, c->stream));
-    const int b = c->tile_buf;  // which half of the list pool this launch appends to
+    const int b = c->tile_buf;  // which half of the list pool / which spill list this launch uses
+    const bool pipelined = c->tiled && c->tile_calibrated;
     if (c->tiled) {
       if (c->apply_pending[b]) {  // the half is free again once its previous apply has finished
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_applied[b], 0));
@@ -442,28 +451,36 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       rp.pool = c->d_pool + (size_t)b * (c->pool_entries / 2);
       CU(c, cudaMemsetAsync(rp.tcount, 0, sizeof(uint32_t) * c->n_lists, c->stream));
     }
+    CU(c, cudaMemsetAsync(c->spill[b].count, 0, sizeof(unsigned int) * 2, c->stream));
     uint64_t want = (count + kChunk - 1) / kChunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
     const size_t dyn = c->tiled ? c->tile_smem : 0;
     render_persistent_kernel<<<grid, kThreadsPerCta, c->render_smem + c->smem_pad + dyn, c->stream>>>(
-        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill);
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
     CU(c, cudaGetLastError());
-    // orbits the warps could not run with enough lanes: finished with grid-wide refill
-    orbit_drain_kernel<<<grid, kThreadsPerCta, dyn, c->stream>>>(rp, c->d_hist, c->d_counters,
-                                                                  c->spill, c->d_spill_next);
-    c->launches += 1;
-    if (c->tiled && c->tile_calibrated) {
-      // apply this launch's lists on the second stream while the next launch renders
-      CU(c, cudaGetLastError());
-      static const bool serial = getenv("BUDDHA_TILE_SERIAL") != nullptr;  // experiment switch
-      cudaStream_t as = serial ? c->stream : c->apply_stream;
+    // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render
+    // kernel of the following launch.
+    static const bool serial = getenv("BUDDHA_TILE_SERIAL") != nullptr;  // experiment switch
+    cudaStream_t side = (pipelined && !serial) ? c->apply_stream : c->stream;
+    if (pipelined) {
       CU(c, cudaEventRecord(c->ev_rendered, c->stream));
-      CU(c, cudaStreamWaitEvent(as, c->ev_rendered, 0));
+      CU(c, cudaStreamWaitEvent(side, c->ev_rendered, 0));
+    }
+    // orbits the warps could not run with enough lanes: finished with grid-wide refill
+    const int dgrid = (grid * kWarpsPerCta + kDrainWarps - 1) / kDrainWarps;
+    const size_t ddyn = c->tiled ? (size_t)c->n_tiles * kDrainWarps * sizeof(uint2) : 0;
+    orbit_drain_kernel<<<dgrid, kDrainWarps * 32, ddyn, side>>>(rp, c->d_hist, c->d_counters,
+                                                                 c->spill[b], c->d_spill_next[b]);
+    c->launches += 1;
+    if (pipelined) {
+      // apply this launch's lists while the next launch renders
+      CU(c, cudaGetLastError());
+      const int agrid = (int)((c->tile_warps + kApplyWarps - 1) / kApplyWarps);
       for (int t = 0; t < c->n_tiles; t++)
-        apply_tile_kernel<<<grid, kThreadsPerCta, 0, as>>>(
+        apply_tile_kernel<<<agrid, kApplyWarps * 32, 0, side>>>(
             c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift);
-      CU(c, cudaEventRecord(c->ev_applied[b], as));
+      CU(c, cudaEventRecord(c->ev_applied[b], side));
       c->apply_pending[b] = true;
       c->tile_buf = b ^ 1;
       c->launches += c->n_tiles;
@@ -494,22 +511,18 @@ static int calibrate_tiles(buddha_ctx *c, uint64_t first, uint64_t count) {
     for (uint32_t w = 0; w < c->tile_warps; w++) tile_pts[t] += cnt[(size_t)t * c->tile_warps + w];
     total += tile_pts[t];
   }
-  std::vector<uint32_t> cap(c->n_lists);
-  std::vector<unsigned long long> base(c->n_lists);
-  unsigned long long pos = 0;
+  std::vector<uint32_t> cap(c->n_tiles), base(c->n_tiles);
+  uint64_t pos = 0;
   for (int t = 0; t < c->n_tiles; t++) {
     double share = total > 0 ? tile_pts[t] / total : 1.0 / c->n_tiles;
     double want = (double)(c->pool_entries / 2) * (0.85 * share + 0.15 / c->n_tiles) / c->tile_warps;
-    uint32_t each = (uint32_t)std::min(want, 4294967040.0);
-    for (uint32_t w = 0; w < c->tile_warps; w++) {
-      cap[(size_t)t * c->tile_warps + w] = each;
-      base[(size_t)t * c->tile_warps + w] = pos;
-      pos += each;
-    }
+    cap[t] = (uint32_t)want;  // the shares sum to 1: the lists fit one pool half (< 2^32 entries)
+    base[t] = (uint32_t)pos;
+    pos += (uint64_t)cap[t] * c->tile_warps;
   }
-  CU(c, cudaMemcpyAsync(c->d_tcap, cap.data(), sizeof(uint32_t) * c->n_lists,
+  CU(c, cudaMemcpyAsync(c->d_tcap, cap.data(), sizeof(uint32_t) * c->n_tiles,
                         cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(c->d_tbase, base.data(), sizeof(unsigned long long) * c->n_lists,
+  CU(c, cudaMemcpyAsync(c->d_tbase, base.data(), sizeof(uint32_t) * c->n_tiles,
                         cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->tile_pts_per_sample = total / (double)count;

@@ -62,9 +62,9 @@ struct RenderParams {
   int32_t tile_shift;           // log2(cells per tile)
   int32_t n_tiles;
   uint32_t n_warps;             // warps of the full persistent grid = lists per tile
-  uint32_t *tcount;             // [tile * n_warps + warp] entries appended so far
-  const uint32_t *tcap;         // [tile * n_warps + warp] capacity of each list
-  const unsigned long long *tbase;  // [tile * n_warps + warp] first pool entry of each list
+  uint32_t *tcount;             // [tile * n_warps + warp] appends ATTEMPTED so far (may exceed cap)
+  const uint32_t *tile_cap;     // [tile] capacity of each of the tile's lists
+  const uint32_t *tile_base;    // [tile] first pool entry of the tile; list w starts at + w * cap
   uint32_t *pool;               // tile-local cell offsets
 };
 
@@ -116,15 +116,11 @@ __device__ __forceinline__ uint4 philox4x32_10(unsigned long long s, const Rende
 }
 
 // _curand_uniform_double_hq (curand_uniform.h:101-105) followed by cudabrot.cu:392-393, scaled by
-// two: returns 2*(u*4-2) = fma(u, 8, -4).  The 53-bit integer is converted with two exact DADDs
-// (magic-number trick) instead of I2F.F64.U64.
+// two: returns 2*(u*4-2) = fma(u, 8, -4).  The 53-bit integer converts exactly (one I2F.F64.U64 on
+// the XU pipe, which this kernel does not use otherwise).
 __device__ __forceinline__ double coord2_from_words(uint32_t x, uint32_t y) {
-  uint32_t lo = x ^ (y << 21);
-  uint32_t hi = y >> 11;
-  double dhi = __hiloint2double(0x45300000, (int)hi);  // 2^84 + hi * 2^32
-  double dlo = __hiloint2double(0x43300000, (int)lo);  // 2^52 + lo
-  double z = __dadd_rn(__dadd_rn(dhi, -(0x1p84 + 0x1p52)), dlo);  // exact: z < 2^53
-  double u = __fma_rn(z, 0x1p-53, 0x1p-54);
+  const unsigned long long z = ((unsigned long long)(y >> 11) << 32) | (x ^ (y << 21));
+  double u = __fma_rn(__ull2double_rn(z), 0x1p-53, 0x1p-54);
   return __fma_rn(u, 8.0, -4.0);
 }
 
@@ -155,37 +151,49 @@ __device__ __forceinline__ bool rejected2(double cx, double cy) {
 // the direct reduction, so list capacity only affects speed, never the result.
 struct Sink {
   uint32_t *hist;
-  uint32_t *tile_cnt;  // shared memory: this warp's append counters, one per tile (or nullptr)
+  uint2 *tile_tab;     // shared memory, one entry per tile: (next pool slot, end of this warp's list)
   uint32_t gwarp;      // global warp index = list column
 };
 
 __device__ __forceinline__ void scatter(const RenderParams &p, const Sink &k, uint32_t idx) {
   if (p.tile_shift) {
-    const uint32_t tile = idx >> p.tile_shift;
-    const uint32_t slot = atomicAdd(k.tile_cnt + tile, 1u);
-    const uint32_t list = tile * p.n_warps + k.gwarp;
-    if (slot < __ldg(p.tcap + list)) {
-      __stcs(p.pool + (__ldg(p.tbase + list) + slot), idx & ((1u << p.tile_shift) - 1u));
+    uint2 *e = k.tile_tab + (idx >> p.tile_shift);
+    const uint32_t slot = atomicAdd(&e->x, 1u);
+    if (slot < e->y) {
+      __stcs(p.pool + slot, idx & ((1u << p.tile_shift) - 1u));
       return;
     }
   }
   red_add_u32(k.hist + idx);
 }
 
-// Per-warp append counters: zero them / reload what an earlier kernel of the same launch left,
-// and publish them for apply_tile_kernel at the end.
-__device__ __forceinline__ void tile_counters_load(const RenderParams &p, const Sink &k, bool zero) {
-  if (!p.tile_shift) return;
-  for (int t = lane_id(); t < p.n_tiles; t += 32)
-    k.tile_cnt[t] = zero ? 0u : p.tcount[(size_t)t * p.n_warps + k.gwarp];
+// Per-warp list table: set it up (mode 0: empty lists, mode 1: continue where an earlier kernel
+// of the same launch stopped) and publish the attempted-append counts for apply_tile_kernel and
+// the calibration (mode 2).  Not inlined (arguments by value): runs once per warp and launch.
+__device__ __noinline__ void tile_table_copy(uint2 *tab, uint32_t *tcount, const uint32_t *tile_cap,
+                                             const uint32_t *tile_base, int n_tiles,
+                                             uint32_t n_warps, uint32_t gwarp, int mode) {
+  __syncwarp();
+#pragma unroll 1
+  for (int t = lane_id(); t < n_tiles; t += 32) {
+    uint32_t *g = tcount + (size_t)t * n_warps + gwarp;
+    const uint32_t cap = tile_cap[t];
+    const uint32_t begin = tile_base[t] + gwarp * cap;
+    if (mode == 2) *g = tab[t].x - begin;
+    else tab[t] = make_uint2(begin + (mode == 0 ? 0u : *g), begin + cap);
+  }
   __syncwarp();
 }
 
+__device__ __forceinline__ void tile_counters_load(const RenderParams &p, const Sink &k, bool zero) {
+  if (p.tile_shift)
+    tile_table_copy(k.tile_tab, p.tcount, p.tile_cap, p.tile_base, p.n_tiles, p.n_warps, k.gwarp,
+                    zero ? 0 : 1);
+}
+
 __device__ __forceinline__ void tile_counters_store(const RenderParams &p, const Sink &k) {
-  if (!p.tile_shift) return;
-  __syncwarp();
-  for (int t = lane_id(); t < p.n_tiles; t += 32)
-    p.tcount[(size_t)t * p.n_warps + k.gwarp] = k.tile_cnt[t];
+  if (p.tile_shift)
+    tile_table_copy(k.tile_tab, p.tcount, p.tile_cap, p.tile_base, p.n_tiles, p.n_warps, k.gwarp, 2);
 }
 
 // ---- binning --------------------------------------------------------------------------------
@@ -358,19 +366,29 @@ struct WarpState {
   uint32_t p_pts, p_inc;
 };
 
-__device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
-  uint32_t v[kCntSlots] = {ws.n_rej, ws.n_hit, 0u, ws.n_acc, ws.steps, ws.p_pts,
-                           ws.p_inc, ws.steps, ws.n_cyc, ws.n_exact};
-#pragma unroll
+// Warp-reduce nine per-lane counters and add them to the global accumulators.  Deliberately not
+// inlined (arguments by value, so the caller's state stays in registers): it runs once per 4096
+// candidates and would otherwise be replicated at every call site.
+__device__ __noinline__ void flush_values(unsigned long long *counters, uint32_t n_rej,
+                                          uint32_t n_hit, uint32_t n_acc, uint32_t e_ref,
+                                          uint32_t e_ref2, uint32_t p_pts, uint32_t p_inc,
+                                          uint32_t e_exec2, uint32_t n_cyc, uint32_t n_exact) {
+  const uint32_t v[kCntSlots] = {n_rej, n_hit, 0u, n_acc, e_ref, p_pts, p_inc, e_ref, n_cyc, n_exact};
+#pragma unroll 1
   for (int k = 0; k < kCntSlots; k++) {
     if (k == kCntTooEarly) continue;  // derived on the host: candidates - the other classes
     unsigned long long x = v[k];
-    if (k == kCntEscapeIters) x += ws.skipped;
-    if (k == kCntExecuted) x += ws.wasted;
+    if (k == kCntEscapeIters) x += e_ref2;
+    if (k == kCntExecuted) x += e_exec2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
     if (lane_id() == 0 && x) atomicAdd(counters + k, x);
   }
+}
+
+__device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
+  flush_values(counters, ws.n_rej, ws.n_hit, ws.n_acc, ws.steps, ws.skipped, ws.p_pts, ws.p_inc,
+               ws.wasted, ws.n_cyc, ws.n_exact);
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 }
@@ -412,13 +430,15 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
   }
 }
 
-// (a) sampler + steps 1..kGenSteps.  One batch = one candidate per lane.
+// (a) sampler + steps 1..kGenSteps (= 2).  One batch = one candidate per lane.  kCommon: max_it >
+// kGenSteps, so both steps count and survivors move on; otherwise the general limit logic runs.
+template <bool kCommon>
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
                                           unsigned long long *counters) {
+  static_assert(kGenSteps == 2, "gen_phase is written for two steps");
   const unsigned lane = lane_id();
   const int allowed = max(0, min(kGenSteps, p.max_it));  // IterateMandelbrot stops at max
-  const bool last = p.max_it <= kGenSteps;               // survivors have run all max iterations
   const bool may_accept = kGenSteps - 1 >= p.min_it;
 #pragma unroll 1
   while (ws.t1_n < 32 && ws.orb_n < 32) {
@@ -443,19 +463,24 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     const bool cand = valid && !rej;
     ws.n_rej += (valid && rej) ? 1u : 0u;
     double x = cx, y = cy;
-    bool alive = cand;
-    int cnt = 0;
-    tested_steps<kGenSteps>(x, y, cx, cy, alive, cnt);
-    const bool esc = cand && !alive && cnt <= allowed;
-    ws.steps += (uint32_t)min(cnt, allowed);
-    const bool surv = cand && !esc;
-    if (last) {
-      ws.n_hit += surv ? 1u : 0u;
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    const bool in1 = cand && !(norm4(x, y) > 16.0);  // still inside after step 1
+    BUDDHA_ZSTEP(x, y, cx, cy);
+    const bool in2 = in1 && !(norm4(x, y) > 16.0);
+    if (kCommon) {
+      ws.steps += cand ? 1u : 0u;
+      ws.steps += in1 ? 1u : 0u;
+      int slot = push_slot(ws.t1_n, in2);
+      if (in2) q.t1.c[slot] = make_double2(cx, cy);
+      if (may_accept) push_orbit(q, ws, cand && !in2 && ((in1 ? 1 : 0) >= p.min_it), cx, cy, in1 ? 2 : 1);
     } else {
-      int slot = push_slot(ws.t1_n, surv);
-      if (surv) q.t1.c[slot] = make_double2(cx, cy);
+      // max_it <= 2: escapes after the limit do not count; whoever is left has hit max
+      const int cnt = in1 ? 2 : 1;  // steps until the escape (if any)
+      const bool esc = cand && !in2 && cnt <= allowed;
+      ws.steps += cand ? (uint32_t)min(cnt, allowed) : 0u;
+      ws.n_hit += (cand && !esc) ? 1u : 0u;
+      if (may_accept) push_orbit(q, ws, esc && (cnt - 1 >= p.min_it), cx, cy, cnt);
     }
-    if (may_accept) push_orbit(q, ws, esc && (cnt - 1 >= p.min_it), cx, cy, cnt);
   }
   __syncwarp();
 }
@@ -491,19 +516,25 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
   bool alive = act;
   int cnt = 0;
   tested_steps<N>(x, y, cx, cy, alive, cnt);
-  const int allowed = min(N, p.max_it - A);  // >= 1: nothing is pushed here once max is reached
-  const bool esc = act && !alive && cnt <= allowed;
-  ws.steps += (uint32_t)min(cnt, allowed);
-  const bool surv = act && !esc;
-  if (p.max_it <= A + N) {
-    ws.n_hit += surv ? 1u : 0u;
-  } else if (kToLate) {
-    push_z(q.late, ws.late_n, surv, cx, cy, x, y, A + N);
+  if (p.max_it > A + N) {
+    // the common case: every step counts, survivors move on
+    ws.steps += (uint32_t)cnt;
+    if (kToLate) {
+      push_z(q.late, ws.late_n, alive, cx, cy, x, y, A + N);
+    } else {
+      int slot = push_slot(ws.t2_n, alive);
+      if (alive) q.t2.c[slot] = make_double2(cx, cy);
+    }
+    if (A + N - 1 >= p.min_it)
+      push_orbit(q, ws, act && !alive && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
   } else {
-    int slot = push_slot(ws.t2_n, surv);
-    if (surv) q.t2.c[slot] = make_double2(cx, cy);
+    // max_it falls inside this tier: escapes after the limit do not count, the rest has hit max
+    const int allowed = p.max_it - A;  // >= 1: nothing is pushed here once max is reached
+    const bool esc = act && !alive && cnt <= allowed;
+    ws.steps += (uint32_t)min(cnt, allowed);
+    ws.n_hit += (act && !esc) ? 1u : 0u;
+    if (A + N - 1 >= p.min_it) push_orbit(q, ws, esc && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
   }
-  if (A + N - 1 >= p.min_it) push_orbit(q, ws, esc && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
   __syncwarp();
 }
 
@@ -542,6 +573,17 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
     push_z(q.late, ws.late_n, cont && !todeep, cx, cy, x, y, nit);
   }
   __syncwarp();
+}
+
+// Checkpoint schedule of the periodicity search: a new checkpoint after 1, 2, 3, 4, 6, 8, 12, 16,
+// 24, ... rounds (ages with at most two significant bits).  A cycle is found once a checkpoint
+// lies on it and the gap to the next checkpoint covers its period (in rounds); the 1.33..1.5
+// spacing costs 10 % fewer iterations on in-set samples than Brent's powers of two (simulated on
+// the config-2 sample distribution: 2054 vs 2280 iterations per in-set sample, ideal 1795).
+__device__ __forceinline__ bool checkpoint_age(unsigned age) {
+  const unsigned low = age & (0u - age);
+  const unsigned rest = age ^ low;
+  return rest == 0u || rest == (low << 1);
 }
 
 // (c) long escape tests.  Each round runs kBlock unchecked steps and tests |z|^2 once.  Because
@@ -589,17 +631,17 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
 #pragma unroll
       for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
       out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
-      const unsigned prev = age++;
+      age++;
       same_x = shortcut && __double_as_longlong(x) == __double_as_longlong(rx);
       tail = age == last;
       const bool fin = act && (out || same_x || tail);
       if (__ballot_sync(kFull, fin)) break;
-      if ((age & prev) == 0u) { rx = x; ry = y; }  // new checkpoint after 1, 2, 4, 8, ... rounds
+      if (checkpoint_age(age)) { rx = x; ry = y; }
     }
     {
       // the checkpoint update of the final round was skipped by the break: compare first
       const bool cyc = same_x && __double_as_longlong(y) == __double_as_longlong(ry);
-      if ((age & (age - 1u)) == 0u) { rx = x; ry = y; }
+      if (checkpoint_age(age)) { rx = x; ry = y; }
       const bool fin = act && (out || cyc || tail);
       int it = it0 + (int)((age - age0) * kBlock);
       if (fin && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
@@ -677,7 +719,7 @@ struct OrbitSpill {
   unsigned int capacity;
 };
 
-// Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles counters per warp.
+// Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles list entries per warp.
 constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSm)
@@ -686,8 +728,8 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ counters, OrbitSpill spill) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpQueues &q = reinterpret_cast<WarpQueues *>(smem_raw)[threadIdx.x >> 5];
-  uint32_t *tile_counters = reinterpret_cast<uint32_t *>(smem_raw + kQueueBytes);
-  const Sink sink = {hist, tile_counters + (threadIdx.x >> 5) * p.n_tiles,
+  uint2 *tile_tab = reinterpret_cast<uint2 *>(smem_raw + kQueueBytes);
+  const Sink sink = {hist, tile_tab + (threadIdx.x >> 5) * p.n_tiles,
                      blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
   tile_counters_load(p, sink, true);
   WarpState ws;
@@ -701,19 +743,26 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
 #pragma unroll 1
   for (;;) {
     // strict priority along the push graph: a phase is reached only when every stack it pushes
-    // to holds < 32 entries
-    if (ws.orb_n >= 32) { orbit_phase(p, q, ws, sink); continue; }
-    if (ws.late_n >= 32) { late_phase(p, q, ws); continue; }
-    if (ws.deep_n >= 32) { deep_phase(p, q, ws, false); continue; }
-    if (ws.t2_n >= 32) { tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n); continue; }
-    if (ws.t1_n >= 32) { tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n); continue; }
-    if (!(ws.exhausted && ws.chunk_off >= ws.chunk_len)) { gen_phase(p, q, ws, cursor, counters); continue; }
-    // the sample range is used up: run the partial stacks dry, upstream first
-    if (ws.t1_n > 0) { tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n); continue; }
-    if (ws.t2_n > 0) { tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n); continue; }
-    if (ws.late_n > 0) { late_phase(p, q, ws); continue; }
-    if (ws.deep_n > 0) { deep_phase(p, q, ws, true); continue; }
-    break;
+    // to holds < 32 entries.  Once the sample range is used up (`dry`) the partial stacks are run
+    // dry, upstream first.
+    const bool dry = ws.exhausted && ws.chunk_off >= ws.chunk_len;
+    const bool dry1 = dry && ws.t1_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
+    if (ws.orb_n >= 32) {
+      orbit_phase(p, q, ws, sink);
+    } else if (ws.late_n >= 32 || (dry2 && ws.late_n > 0)) {
+      late_phase(p, q, ws);
+    } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
+      deep_phase(p, q, ws, dry3);
+    } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
+      tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n);
+    } else if (ws.t1_n >= 32 || (dry && ws.t1_n > 0)) {
+      tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n);
+    } else if (!dry) {
+      if (p.max_it > kGenSteps) gen_phase<true>(p, q, ws, cursor, counters);
+      else gen_phase<false>(p, q, ws, cursor, counters);
+    } else {
+      break;
+    }
   }
   // leftovers (< 32 accepted samples): hand them to the grid-wide list
   if (ws.orb_n > 0) {
@@ -732,15 +781,20 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   flush_counters(ws, counters);
 }
 
-// Finishes the spilled orbits: every lane pulls the next entry from the grid-wide list.
-__global__ void __launch_bounds__(kThreadsPerCta)
+// Finishes the spilled orbits: every lane pulls the next entry from the grid-wide list.  Small
+// CTAs (kDrainWarps warps), so that in a pipeline of launches the drain of launch k fits next to
+// the resident render CTAs of launch k+1; warp w continues list column w of the render kernel.
+constexpr int kDrainWarps = 4;
+
+__global__ void __launch_bounds__(kDrainWarps * 32)
 orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
                    unsigned long long *__restrict__ counters, OrbitSpill spill,
                    unsigned int *__restrict__ next) {
   const unsigned total = min(*spill.count, spill.capacity);
-  extern __shared__ uint32_t tile_counters[];
-  const Sink sink = {hist, tile_counters + (threadIdx.x >> 5) * p.n_tiles,
-                     blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
+  extern __shared__ uint2 tile_tab[];
+  const uint32_t gwarp = blockIdx.x * kDrainWarps + (threadIdx.x >> 5);
+  if (p.tile_shift && gwarp >= p.n_warps) return;  // no list column to append to
+  const Sink sink = {hist, tile_tab + (threadIdx.x >> 5) * p.n_tiles, gwarp};
   tile_counters_load(p, sink, false);  // continue the lists where the render kernel stopped
   WarpState ws;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
@@ -772,16 +826,19 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
 // Applies the lists of ONE tile: warp w owns list (t, w).  One launch per tile keeps every
 // reduction of the launch inside the same 64 MB of histogram, which stays L2-resident (a single
 // launch walking all tiles lets the warps drift apart and measured 66 % L2 misses); list entries
-// are read once, coalesced, with a streaming (evict-first) load.
-__global__ void __launch_bounds__(kThreadsPerCta)
+// are read once, coalesced, with a streaming (evict-first) load.  CTAs are small (4 warps, 32
+// registers) so that they fit next to the resident render CTAs of the following launch.
+constexpr int kApplyWarps = 4;
+
+__global__ void __launch_bounds__(kApplyWarps * 32)
 apply_tile_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ tcount,
-                  const uint32_t *__restrict__ tcap, const unsigned long long *__restrict__ tbase,
+                  const uint32_t *__restrict__ tile_cap, const uint32_t *__restrict__ tile_base,
                   const uint32_t *__restrict__ pool, int t, uint32_t n_warps, int tile_shift) {
-  const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const uint32_t w = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
   if (w >= n_warps) return;
-  const size_t list = (size_t)t * n_warps + w;
-  const uint32_t n = min(tcount[list], tcap[list]);
-  const uint32_t *src = pool + tbase[list];
+  const uint32_t cap = tile_cap[t];
+  const uint32_t n = min(tcount[(size_t)t * n_warps + w], cap);
+  const uint32_t *src = pool + (tile_base[t] + w * cap);
   uint32_t *tile = hist + ((size_t)t << tile_shift);
   uint32_t i = lane_id();
   for (; i + 96 < n; i += 128) {
