@@ -672,17 +672,36 @@ struct OrbitLane {
   int n;
 };
 
+// One recorded step.  The common path is branch-free (the increment is a predicated reduction), so
+// the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
+// the rare exact-binning case branches.
 __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                            const Sink &hist) {
   BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
-  if (o.act) {
-    bool exact = false;
-    bool in = p.fast_bin ? bin_point(o.x, o.y, p, hist, &exact)
-                         : (exact = true, bin_exact(o.x, o.y, p, hist));
-    ws.p_inc += in ? 1u : 0u;
-    ws.n_exact += exact ? 1u : 0u;
-    if (--o.n == 0) { o.act = false; o.cx = o.cy = o.x = o.y = 0.0; }
+  // division-free binning, see bin_point
+  const double tch = __fma_rn(o.x, p.inv_half_re, p.c0_hi_re);
+  const double tcl = __fma_rn(o.x, p.inv_half_re, p.c0_lo_re);
+  const double trh = __fma_rn(o.y, p.inv_half_im, p.c0_hi_im);
+  const double trl = __fma_rn(o.y, p.inv_half_im, p.c0_lo_im);
+  const uint32_t ch = (uint32_t)__double2loint(tch), cl = (uint32_t)__double2loint(tcl);
+  const uint32_t rh = (uint32_t)__double2loint(trh), rl = (uint32_t)__double2loint(trl);
+  const bool inrange = ((uint32_t)__double2hiint(tch) == kBinHiWord) &
+                       ((uint32_t)__double2hiint(trh) == kBinHiWord);
+  const bool same = ((((ch ^ cl) | (rh ^ rl)) >> kBinFracBits) == 0u) &
+                    ((uint32_t)__double2hiint(tcl) == kBinHiWord) &
+                    ((uint32_t)__double2hiint(trl) == kBinHiWord);
+  const uint32_t col = ch >> kBinFracBits, row = rh >> kBinFracBits;
+  const bool fast = o.act && p.fast_bin != 0;
+  const bool hit = fast && inrange && same && col < (uint32_t)p.w && row < (uint32_t)p.h;
+  const bool slow = o.act && (p.fast_bin == 0 || (inrange && !same));
+  if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
+  ws.p_inc += hit ? 1u : 0u;
+  if (slow) {
+    ws.n_exact += 1u;
+    ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
   }
+  o.n -= o.act ? 1 : 0;
+  o.act = o.act && o.n != 0;
 }
 
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
@@ -704,7 +723,8 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     }
     unsigned am = __ballot_sync(kFull, o.act);
     if (__popc(am) < kOrbExit) break;
-    orbit_step(p, o, ws, hist);
+    orbit_step(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
+    orbit_step(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
   if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
@@ -817,6 +837,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
       more = base + __popc(need) < total;
     }
     if (__ballot_sync(kFull, o.act) == 0u) break;
+    orbit_step(p, o, ws, sink);
     orbit_step(p, o, ws, sink);
   }
   tile_counters_store(p, sink);
