@@ -9,7 +9,7 @@ import os
 import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libbuddha.so")
+LIB_PATH = os.environ.get("BUDDHA_LIB") or os.path.join(PKG_DIR, "libbuddha.so")  # override: A/B runs
 CLI_PATH = os.path.join(PKG_DIR, "bin", "cudabrot")
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
