@@ -42,6 +42,10 @@ WORKLOADS = {
     "cfg5c": (10000, 10000, 20000, 20, FULL, 1 << 32),
 }
 REFERENCE_PASS = 13107200  # 512 blocks * 512 threads * 50 samples, cudabrot.cu:20,23,34
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE render_persistent_kernel launch over 2^30
+# samples, from the `ncu --set full` captures summarised in profiles/r01_summary.md
+NCU_DRAM_BYTES_PER_2P30_LAUNCH = {"cfg1": 4037888 + 1280, "cfg2": 37888 + 256,
+                                  "cfg3": 208894976 + 5066775000}
 METRIC = "candidate samples/sec"
 
 
@@ -50,19 +54,22 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; only samples taken between
+    mark_start() and stop() (the timed region) are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+        self.rows, self.proc, self.device, self.t_start = [], None, device, None
 
     def start(self):
+        """Launch the sampler (nvidia-smi takes a while to produce its first line: call this well
+        before the timed region)."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -70,9 +77,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t_start = time.perf_counter()
 
     def stop(self):
+        t_end = time.perf_counter()
         if self.proc:
             self.proc.terminate()
             try:
@@ -81,7 +92,9 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, pw, reasons = [], 0, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.t_start is not None and not (self.t_start <= t <= t_end + 0.05):
+                continue
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1])); pw.append(float(r[2]))
             except (ValueError, IndexError):
@@ -210,6 +223,10 @@ def native_arm(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # ---- warm-up (untimed), incl. one collective so NCCL is initialised -------------------
     for k in range(args.warmup):
         f, n = step_range(k, rank, world, per_gpu, first=1 << 56)
@@ -222,10 +239,8 @@ def native_arm(args, wl, rank, world, local_rank):
     fp64_peak = r.probe_fp64_peak()
 
     # ---- timed region: K steps (+ the one merge), device-timed per step ---------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.mark_start()
     wall0 = time.perf_counter()
     dev_ms = 0.0
     for k in range(args.steps):
@@ -305,7 +320,12 @@ def native_arm(args, wl, rank, world, local_rank):
     roofline = {
         "bound": "fp64-pipe", "unit": "Tlane-instr/s",
         "achieved": lane_exec / t_s / 1e12, "peak": fp64_peak / 1e12,
-        "frac": lane_exec / t_s / fp64_peak, "traffic": None,
+        "frac": lane_exec / t_s / fp64_peak,
+        "traffic": NCU_DRAM_BYTES_PER_2P30_LAUNCH.get(args.workload),
+        "traffic_note": "DRAM bytes (read+write) of one render_persistent_kernel launch over 2^30 "
+                        "samples of this workload, ncu --set full (profiles/r01_summary.md); the "
+                        "kernel is FP64/issue bound, its algorithmic memory traffic is 4 B per "
+                        "in-canvas increment at L2",
         "peak_source": "in-run independent-DFMA probe (buddha_probe_fp64_peak); MEASURED_PEAKS.json "
                        "has no FP64 figure",
         "numerator": "reference-dataflow FP64 instructions (14*S + 8*E + 8*P, SURVEY.md 8(d)) with "
