@@ -675,9 +675,8 @@ struct OrbitLane {
 // One recorded step.  The common path is branch-free (the increment is a predicated reduction), so
 // the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
 // the rare exact-binning case branches.
-__device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
-                                           const Sink &hist) {
-  BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
+__device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane &o, WarpState &ws,
+                                          const Sink &hist) {
   // division-free binning, see bin_point
   const double tch = __fma_rn(o.x, p.inv_half_re, p.c0_hi_re);
   const double tcl = __fma_rn(o.x, p.inv_half_re, p.c0_lo_re);
@@ -700,6 +699,12 @@ __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, 
     ws.n_exact += 1u;
     ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
   }
+}
+
+__device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
+                                           const Sink &hist) {
+  BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
+  orbit_bin(p, o, ws, hist);
   o.n -= o.act ? 1 : 0;
   o.act = o.act && o.n != 0;
 }
@@ -801,9 +806,16 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   flush_counters(ws, counters);
 }
 
-// Finishes the spilled orbits: every lane pulls the next entry from the grid-wide list.  Small
-// CTAs (kDrainWarps warps), so that in a pipeline of launches the drain of launch k fits next to
-// the resident render CTAs of launch k+1; warp w continues list column w of the render kernel.
+// Finishes the spilled orbits.  The leftovers are few but up to max_it steps long, so their cost is
+// latency: a lane stepping its own orbit needs ~360 cycles per recorded point (z-step, binning and
+// bookkeeping in one dependent instruction stream) although the z-chain itself is 17.7 cycles per
+// step.  So an orbit is given to a GROUP of g lanes (g = 1..32, the largest power of two for which
+// all orbits still fit the grid twice over): every lane of the group runs the same z-chain, lane k
+// keeps point k of each block of g steps, and the g points are binned at once -- about
+// (17.7 g + 300) / g cycles per point.  The redundant FP64 work is irrelevant at this volume.
+// Small CTAs (kDrainWarps warps), so that in a pipeline of launches the drain of launch k fits
+// next to the resident render CTAs of launch k+1; warp w continues list column w of the render
+// kernel (tiling).
 constexpr int kDrainWarps = 4;
 
 __global__ void __launch_bounds__(kDrainWarps * 32)
@@ -819,26 +831,46 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   WarpState ws;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
-  OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
-  bool more = true;
+
+  int g = 32;
+  {
+    unsigned long long warps = (unsigned long long)gridDim.x * kDrainWarps;
+    if (p.tile_shift && warps > p.n_warps) warps = p.n_warps;
+    const unsigned long long lanes = 2ull * 32ull * warps;
+    while (g > 1 && (unsigned long long)total * g > lanes) g >>= 1;
+  }
+  const int lane = (int)lane_id();
+  const int sub = lane & (g - 1), leader = lane & ~(g - 1);
+  double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
+  int n = 0;          // steps this group's orbit still has to record (group-uniform)
+  bool more = true;   // the list may still hold entries (group-uniform)
 #pragma unroll 1
   for (;;) {
-    unsigned need = __ballot_sync(kFull, !o.act);
-    if (need && more) {
+    const unsigned needm = __ballot_sync(kFull, n <= 0 && more && sub == 0);
+    if (needm) {
       unsigned base = 0;
-      if (lane_id() == 0) base = atomicAdd(next, (unsigned)__popc(need));
+      if (lane == 0) base = atomicAdd(next, (unsigned)__popc(needm));
       base = __shfl_sync(kFull, base, 0);
-      unsigned idx = base + __popc(need & lanemask_lt());
-      if (!o.act && idx < total) {
-        double4 e = spill.entries[idx];
-        o.cx = e.x; o.cy = e.y; o.x = e.z; o.y = e.w; o.n = spill.steps[idx];
-        o.act = true;
+      unsigned idx = base + __popc(needm & lanemask_lt());  // meaningful on the leaders
+      idx = __shfl_sync(kFull, idx, leader);
+      if (n <= 0 && more) {
+        if (idx < total) {
+          const double4 e = spill.entries[idx];
+          cx = e.x; cy = e.y; x = e.z; y = e.w; n = spill.steps[idx];
+        } else {
+          more = false;
+        }
       }
-      more = base + __popc(need) < total;
     }
-    if (__ballot_sync(kFull, o.act) == 0u) break;
-    orbit_step(p, o, ws, sink);
-    orbit_step(p, o, ws, sink);
+    if (__ballot_sync(kFull, n > 0) == 0u) break;
+    OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, 1};
+#pragma unroll 1
+    for (int k = 0; k < g; k++) {
+      BUDDHA_ZSTEP(x, y, cx, cy);
+      if (sub == k) { o.x = x; o.y = y; }
+    }
+    orbit_bin(p, o, ws, sink);
+    n -= g;
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
