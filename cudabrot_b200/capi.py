@@ -17,6 +17,7 @@ F_NO_SHORTCUT = 1 << 0
 F_SIMPLE_KERNEL = 1 << 1
 F_EXACT_BINNING = 1 << 2
 F_FORCE_TILED = 1 << 3
+F_BURNING_SHIP = 1 << 4
 
 ERRORS = {0: "OK", 1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ESIZE", 5: "ENCCL", 6: "ENODEV"}
 

@@ -122,6 +122,7 @@ void fill_render_params(buddha_ctx *c) {
   r.inv_half_im = fi.inv_half; r.c0_lo_im = fi.c0_lo; r.c0_hi_im = fi.c0_hi;
   r.max_it = p.max_iterations; r.min_it = p.min_iterations;
   r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
+  r.ship = (p.flags & BUDDHA_F_BURNING_SHIP) ? 1 : 0;
   uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
   for (int i = 0; i < 10; i++) {
     r.key0[i] = k0; r.key1[i] = k1;
@@ -274,12 +275,14 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   // the work stacks are dynamic shared memory (110 KB per CTA: opt-in above 48 KB)
   c->render_smem = kQueueBytes;
   if (const char *e = getenv("BUDDHA_PAD_SMEM")) c->smem_pad = (size_t)atoi(e);  // occupancy experiments
-  cudaError_t st = cudaFuncSetAttribute(render_persistent_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const bool ship = (p->flags & BUDDHA_F_BURNING_SHIP) != 0;
+  const void *render_fn = ship ? (const void *)render_persistent_kernel<true>
+                               : (const void *)render_persistent_kernel<false>;
+  cudaError_t st = cudaFuncSetAttribute(render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(kQueueBytes + c->smem_pad + 8192));
   if (st == cudaSuccess)
-    st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel,
-                                                       kThreadsPerCta, c->render_smem + c->smem_pad);
+    st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_fn, kThreadsPerCta,
+                                                       c->render_smem + c->smem_pad);
   if (st != cudaSuccess || per_sm < 1) {
     free(c);
     return fail(nullptr, BUDDHA_ECUDA, "render kernel not launchable on device %d: %s", p->device,
@@ -337,8 +340,7 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       }
       // the per-warp append counters are dynamic shared memory: keep the grid one resident wave
       int per_sm_tiled = 0;
-      CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tiled, render_persistent_kernel,
-                                                        kThreadsPerCta,
+      CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tiled, render_fn, kThreadsPerCta,
                                                         c->render_smem + c->smem_pad + c->tile_smem));
       if (per_sm_tiled >= 1) c->grid = per_sm_tiled * c->sm_count;
       c->tile_warps = (uint32_t)c->grid * kWarpsPerCta;
@@ -456,8 +458,13 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
     const size_t dyn = c->tiled ? c->tile_smem : 0;
-    render_persistent_kernel<<<grid, kThreadsPerCta, c->render_smem + c->smem_pad + dyn, c->stream>>>(
-        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
+    const size_t rsmem = c->render_smem + c->smem_pad + dyn;
+    if (rp.ship)
+      render_persistent_kernel<true><<<grid, kThreadsPerCta, rsmem, c->stream>>>(
+          rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
+    else
+      render_persistent_kernel<false><<<grid, kThreadsPerCta, rsmem, c->stream>>>(
+          rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
     CU(c, cudaGetLastError());
     // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render
     // kernel of the following launch.
@@ -470,8 +477,12 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     // orbits the warps could not run with enough lanes: finished with grid-wide refill
     const int dgrid = (grid * kWarpsPerCta + kDrainWarps - 1) / kDrainWarps;
     const size_t ddyn = c->tiled ? (size_t)c->n_tiles * kDrainWarps * sizeof(uint2) : 0;
-    orbit_drain_kernel<<<dgrid, kDrainWarps * 32, ddyn, side>>>(rp, c->d_hist, c->d_counters,
-                                                                 c->spill[b], c->d_spill_next[b]);
+    if (rp.ship)
+      orbit_drain_kernel<true><<<dgrid, kDrainWarps * 32, ddyn, side>>>(
+          rp, c->d_hist, c->d_counters, c->spill[b], c->d_spill_next[b]);
+    else
+      orbit_drain_kernel<false><<<dgrid, kDrainWarps * 32, ddyn, side>>>(
+          rp, c->d_hist, c->d_counters, c->spill[b], c->d_spill_next[b]);
     c->launches += 1;
     if (pipelined) {
       // apply this launch's lists while the next launch renders

@@ -56,6 +56,7 @@ struct RenderParams {
   int32_t fast_bin;
   int32_t max_it, min_it;
   int32_t shortcut;
+  int32_t ship;                 // burning-ship variant (only the simple kernel reads this at run time)
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
   // tile-binned scatter for histograms much larger than L2 (0 = off, see scatter())
@@ -86,15 +87,19 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-// One step of z <- z^2 + c on the scaled state (4 FP64 instructions).
-#define BUDDHA_ZSTEP(x, y, cx, cy)              \
-  do {                                          \
-    double a4_ = __dmul_rn((y), (y));           \
-    double b4_ = __fma_rn((x), (x), -a4_);      \
-    double yn_ = __fma_rn((x), (y), (cy));      \
-    (x) = __fma_rn(b4_, 0.5, (cx));             \
-    (y) = yn_;                                  \
-  } while (0)
+// One step of z <- z^2 + c on the scaled state (4 FP64 instructions).  kShip: the burning-ship
+// variant (RENDER_BURNING_SHIP, cudabrot.cu:15-17, :327-330, :353-356), real = |real|, imag =
+// |imag| before the step -- only the cross term sees the difference, as operand modifiers
+// (the reference's own SASS for that build: DADD |re|,|re|; DFMA r2,|im|,c_im).
+template <bool kShip>
+__device__ __forceinline__ void zstep(double &x, double &y, double cx, double cy) {
+  const double a4 = __dmul_rn(y, y);
+  const double b4 = __fma_rn(x, x, -a4);
+  const double yn = kShip ? __fma_rn(fabs(x), fabs(y), cy) : __fma_rn(x, y, cy);
+  x = __fma_rn(b4, 0.5, cx);
+  y = yn;
+}
+#define BUDDHA_ZSTEP(x, y, cx, cy) zstep<kShip>((x), (y), (cx), (cy))
 
 // 4 * (re^2 + im^2) with the reference's rounding order (cudabrot.cu:336).
 __device__ __forceinline__ double norm4(double x, double y) {
@@ -263,11 +268,12 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
     bool card = __dmul_rn(q, __dadd_rn(q0, q)) < __dmul_rn(i2, 0.25);
     double t = __dadd_rn(cre, 1.0);
     bool bulb = __fma_rn(t, t, i2) < 0.0625;
-    if (card || bulb) { n_rej++; continue; }
+    if (!p.ship && (card || bulb)) { n_rej++; continue; }
     // cudabrot.cu:319-340
     double re = cre, im = cim;
     int i = p.max_it;
     for (int k = 0; k < p.max_it; k++) {
+      if (p.ship) { re = fabs(re); im = fabs(im); }
       double t1 = __dmul_rn(im, im);
       double t2 = __fma_rn(re, re, -t1);
       double r2 = __dadd_rn(re, re);
@@ -282,6 +288,7 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
     // cudabrot.cu:347-365
     re = cre; im = cim;
     for (;;) {
+      if (p.ship) { re = fabs(re); im = fabs(im); }
       double t1 = __dmul_rn(im, im);
       double t2 = __fma_rn(re, re, -t1);
       double r2 = __dadd_rn(re, re);
@@ -418,7 +425,7 @@ __device__ __forceinline__ void push_orbit(WarpQueues &q, WarpState &ws, bool ac
 // N steps with the exact per-step escape test (cudabrot.cu:331-338) for all lanes at once.
 // *cnt = steps a lane ran while it had not escaped (the escaping step included); `alive` on
 // return: never escaped.  A step limit below N is applied by the caller afterwards.
-template <int N>
+template <bool kShip, int N>
 __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, double cy,
                                              bool &alive, int &cnt) {
 #pragma unroll
@@ -432,7 +439,7 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
 
 // (a) sampler + steps 1..kGenSteps (= 2).  One batch = one candidate per lane.  kCommon: max_it >
 // kGenSteps, so both steps count and survivors move on; otherwise the general limit logic runs.
-template <bool kCommon>
+template <bool kShip, bool kCommon>
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
                                           unsigned long long *counters) {
@@ -459,7 +466,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     uint4 r = philox4x32_10(ws.chunk_base + o, p);
     const double cx = coord2_from_words(r.x, r.y);
     const double cy = coord2_from_words(r.z, r.w);
-    const bool rej = rejected2(cx, cy);
+    const bool rej = kShip ? false : rejected2(cx, cy);  // cudabrot.cu:397-399
     const bool cand = valid && !rej;
     ws.n_rej += (valid && rej) ? 1u : 0u;
     double x = cx, y = cy;
@@ -501,7 +508,7 @@ __device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pre
 // (b) one tier of the escape test: pops up to 32 candidates that survived A steps, re-computes
 // those steps from c (no tests needed: they are known not to escape), runs steps A+1..A+N with the
 // per-step test.  kToLate = false: survivors go to t2 as c only; true: to `late` with their state.
-template <int A, int N, bool kToLate>
+template <bool kShip, int A, int N, bool kToLate>
 __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            CStack &src, int &src_n) {
   const int take = min(src_n, 32);
@@ -515,7 +522,7 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
   for (int k = 0; k < A; k++) BUDDHA_ZSTEP(x, y, cx, cy);
   bool alive = act;
   int cnt = 0;
-  tested_steps<N>(x, y, cx, cy, alive, cnt);
+  tested_steps<kShip, N>(x, y, cx, cy, alive, cnt);
   if (p.max_it > A + N) {
     // the common case: every step counts, survivors move on
     ws.steps += (uint32_t)cnt;
@@ -541,6 +548,7 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
 // (b') 16 per-step-tested steps from a stored state.  Entries: tier-2 survivors (it = 14), samples
 // handed back by deep (certain to escape within kBlock steps), tails (fewer than kBlock steps left
 // below max), samples that deep cannot take (|c| too close to 2, or deep full right now).
+template <bool kShip>
 __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q, WarpState &ws) {
   const int take = min(ws.late_n, 32);
   const bool act = (int)lane_id() < take;
@@ -556,7 +564,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   const bool deep_room = ws.deep_n < 32;
   bool alive = act;
   int cnt = 0;
-  tested_steps<kLateSteps>(x, y, cx, cy, alive, cnt);
+  tested_steps<kShip, kLateSteps>(x, y, cx, cy, alive, cnt);
   const int allowed = min(kLateSteps, p.max_it - it);  // >= 1 for every stored entry
   const bool esc = act && !alive && cnt <= allowed;
   ws.steps += act ? (uint32_t)min(cnt, allowed) : 0u;
@@ -590,6 +598,7 @@ __device__ __forceinline__ bool checkpoint_age(unsigned age) {
 // |c| <= 2 here, an orbit that leaves the radius-2 disc cannot re-enter it,
 // so "escaped somewhere in the round" <=> "outside at the end of the round".  A state that
 // repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (exact shortcut).
+template <bool kShip>
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            bool drain) {
   const int max_it = p.max_it;
@@ -701,6 +710,7 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane
   }
 }
 
+template <bool kShip>
 __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                            const Sink &hist) {
   BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
@@ -709,6 +719,7 @@ __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, 
   o.act = o.act && o.n != 0;
 }
 
+template <bool kShip>
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                             const Sink &hist) {
   OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
@@ -728,8 +739,8 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     }
     unsigned am = __ballot_sync(kFull, o.act);
     if (__popc(am) < kOrbExit) break;
-    orbit_step(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
-    orbit_step(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
+    orbit_step<kShip>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
+    orbit_step<kShip>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
   if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
@@ -747,6 +758,7 @@ struct OrbitSpill {
 // Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles list entries per warp.
 constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 
+template <bool kShip>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSm)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
@@ -773,18 +785,18 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     const bool dry = ws.exhausted && ws.chunk_off >= ws.chunk_len;
     const bool dry1 = dry && ws.t1_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
     if (ws.orb_n >= 32) {
-      orbit_phase(p, q, ws, sink);
+      orbit_phase<kShip>(p, q, ws, sink);
     } else if (ws.late_n >= 32 || (dry2 && ws.late_n > 0)) {
-      late_phase(p, q, ws);
+      late_phase<kShip>(p, q, ws);
     } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
-      deep_phase(p, q, ws, dry3);
+      deep_phase<kShip>(p, q, ws, dry3);
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
-      tier_phase<kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n);
+      tier_phase<kShip, kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n);
     } else if (ws.t1_n >= 32 || (dry && ws.t1_n > 0)) {
-      tier_phase<kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n);
+      tier_phase<kShip, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n);
     } else if (!dry) {
-      if (p.max_it > kGenSteps) gen_phase<true>(p, q, ws, cursor, counters);
-      else gen_phase<false>(p, q, ws, cursor, counters);
+      if (p.max_it > kGenSteps) gen_phase<kShip, true>(p, q, ws, cursor, counters);
+      else gen_phase<kShip, false>(p, q, ws, cursor, counters);
     } else {
       break;
     }
@@ -818,6 +830,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
 // kernel (tiling).
 constexpr int kDrainWarps = 4;
 
+template <bool kShip>
 __global__ void __launch_bounds__(kDrainWarps * 32)
 orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
                    unsigned long long *__restrict__ counters, OrbitSpill spill,

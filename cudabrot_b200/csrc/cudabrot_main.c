@@ -11,6 +11,7 @@
  *   --seed S          Philox key (default 1337 = the reference's DEFAULT_RNG_SEED, cudabrot.cu:37)
  *   --gpus G          use devices d..d+G-1, disjoint sample ranges, one ncclReduce at the end
  *   --no-shortcut     disable the exact periodicity shortcut (identical output, slower)
+ *   --burning-ship    the reference's compile-time RENDER_BURNING_SHIP variant (cudabrot.cu:15-17)
  * With -s FILE the next sample index is kept in FILE.cursor so a resumed run continues the stream
  * instead of replaying it (the reference re-seeds with 1337 and replays).
  */
@@ -125,6 +126,7 @@ static void PrintUsage(char *program_name) {
     "  --seed <S>: Philox key. Defaults to 1337.\n"
     "  --gpus <G>: Use G GPUs starting at -d; histograms are summed at the end.\n"
     "  --no-shortcut: Disable the exact periodicity shortcut (same output).\n"
+    "  --burning-ship: Render the burning ship fractal (RENDER_BURNING_SHIP in the reference).\n"
     "");
   exit(0);
 }
@@ -258,6 +260,7 @@ static void ParseArguments(int argc, char **argv) {
       continue;
     }
     if (strcmp(a, "--no-shortcut") == 0) { g.params.flags |= BUDDHA_F_NO_SHORTCUT; continue; }
+    if (strcmp(a, "--burning-ship") == 0) { g.params.flags |= BUDDHA_F_BURNING_SHIP; continue; }
     printf("Invalid argument: %s\n", a);
     PrintUsage(argv[0]);
   }

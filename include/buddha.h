@@ -39,6 +39,9 @@ enum {
 #define BUDDHA_F_SIMPLE_KERNEL (1u << 1) /* one-sample-per-thread debug kernel, reference dataflow */
 #define BUDDHA_F_EXACT_BINNING (1u << 2) /* always bin with IEEE divisions (same output)           */
 #define BUDDHA_F_FORCE_TILED   (1u << 3) /* tile-binned scatter even for small histograms (tests)  */
+#define BUDDHA_F_BURNING_SHIP  (1u << 4) /* RENDER_BURNING_SHIP (cudabrot.cu:15-17, :327-330,
+                                            :353-356, :397-399): |re|, |im| before every step, no
+                                            cardioid/bulb test; a compile-time switch there     */
 
 /* Canvas + iteration limits: FractalDimensions (cudabrot.cu:46-58) and IterationControl (:62-67),
  * plus what the reference hard-codes (seed, :37) or keeps in its global struct (device, :72). */

@@ -96,10 +96,29 @@ int oracle_rejected(double real, double imag) {
 
 #define ESCAPED(re, im) (FMA((im), (im), (re) * (re)) > 4.0) /* DMUL, DFMA, DSETP */
 
+/* RENDER_BURNING_SHIP (cudabrot.cu:15-17, :327-330, :353-356): real = fabs(real), imag =
+ * fabs(imag) before the step.  SASS of that build (sm_100a, CUDA 12.9): DMUL im,im; DADD |re|,|re|;
+ * DFMA re,re,-t1; DFMA r2,|im|,c_im; DADD c_re,t2 -- the same contraction, |.| as operand
+ * modifiers. */
+#define STEP_SHIP(re, im, cre, cim)                             \
+  do {                                                          \
+    (re) = fabs(re); (im) = fabs(im);                           \
+    STEP(re, im, cre, cim);                                     \
+  } while (0)
+
 int oracle_escape_iterations(double c_real, double c_imag, int max_iterations) {
   double re = c_real, im = c_imag;
   for (int i = 0; i < max_iterations; i++) {
     STEP(re, im, c_real, c_imag);
+    if (ESCAPED(re, im)) return i;
+  }
+  return max_iterations;
+}
+
+int oracle_escape_iterations_ship(double c_real, double c_imag, int max_iterations) {
+  double re = c_real, im = c_imag;
+  for (int i = 0; i < max_iterations; i++) {
+    STEP_SHIP(re, im, c_real, c_imag);
     if (ESCAPED(re, im)) return i;
   }
   return max_iterations;
@@ -157,13 +176,16 @@ static inline void sink_add(sink_t *s, int64_t idx) {
 }
 
 static void render_range(const oracle_dims *d, int max_it, int min_it, uint64_t seed,
-                         uint64_t first, uint64_t count, sink_t *sink, oracle_counters *c) {
+                         uint64_t first, uint64_t count, sink_t *sink, oracle_counters *c,
+                         int ship) {
   for (uint64_t k = 0; k < count; k++) {
     double cre, cim;
     oracle_sample(seed, first + k, &cre, &cim);
     c->candidates++;
-    if (oracle_rejected(cre, cim)) { c->rejected++; continue; }
-    int i = oracle_escape_iterations(cre, cim, max_it);
+    /* cudabrot.cu:397-399: no cardioid/bulb test in the burning-ship build */
+    if (!ship && oracle_rejected(cre, cim)) { c->rejected++; continue; }
+    int i = ship ? oracle_escape_iterations_ship(cre, cim, max_it)
+                 : oracle_escape_iterations(cre, cim, max_it);
     if (i >= max_it) { c->hit_max++; c->escape_iters += (uint64_t)(max_it > 0 ? max_it : 0); continue; }
     c->escape_iters += (uint64_t)i + 1u;
     if (i < min_it) { c->too_early++; continue; }
@@ -171,7 +193,7 @@ static void render_range(const oracle_dims *d, int max_it, int min_it, uint64_t 
     /* IterateAndRecord, cudabrot.cu:347-365 */
     double re = cre, im = cim;
     for (;;) {
-      STEP(re, im, cre, cim);
+      if (ship) STEP_SHIP(re, im, cre, cim); else STEP(re, im, cre, cim);
       c->orbit_points++;
       int64_t idx;
       if (bin_point(re, im, d, &idx)) { sink_add(sink, idx); c->increments++; }
@@ -197,6 +219,13 @@ int oracle_max_threads(void) {
 int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, uint64_t seed,
                   uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
                   int threads) {
+  return oracle_render_ex(d, max_iterations, min_iterations, seed, first, count, hist, counters,
+                          threads, 0);
+}
+
+int oracle_render_ex(const oracle_dims *d, int max_iterations, int min_iterations, uint64_t seed,
+                     uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
+                     int threads, int burning_ship) {
   int nt = threads > 0 ? threads : oracle_max_threads();
   size_t cells = (size_t)d->w * (size_t)d->h;
   oracle_counters total;
@@ -225,7 +254,8 @@ int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, 
     for (uint64_t ci = 0; ci < nchunks; ci++) {
       uint64_t lo = ci * chunk;
       uint64_t n = (count - lo < chunk) ? (count - lo) : chunk;
-      render_range(d, max_iterations, min_iterations, seed, first + lo, n, &sink, &local);
+      render_range(d, max_iterations, min_iterations, seed, first + lo, n, &sink, &local,
+                   burning_ship);
     }
 #ifdef _OPENMP
 #pragma omp critical
@@ -240,6 +270,18 @@ int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, 
   }
   if (counters) *counters = total;
   return nt;
+}
+
+void oracle_classify_ship(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                          int32_t *out_iters) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    out_iters[k] = oracle_escape_iterations_ship(cre, cim, max_iterations);
+  }
 }
 
 void oracle_classify(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
@@ -328,6 +370,19 @@ int oracle_escape_iterations_scaled(double c_real, double c_imag, int max_iterat
   return max_iterations;
 }
 
+int oracle_escape_iterations_scaled_ship(double c_real, double c_imag, int max_iterations) {
+  double cx = c_real * 2.0, cy = c_imag * 2.0, x = cx, y = cy;
+  for (int i = 0; i < max_iterations; i++) {
+    double a4 = y * y;
+    double b4 = FMA(x, x, -a4);
+    double yn = FMA(fabs(x), fabs(y), cy);
+    x = FMA(b4, 0.5, cx);
+    y = yn;
+    if (FMA(y, y, x * x) > 16.0) return i;
+  }
+  return max_iterations;
+}
+
 int oracle_rejected_scaled(double c_real, double c_imag) {
   double cx = c_real * 2.0, cy = c_imag * 2.0;
   double i2 = cy * cy;
@@ -401,6 +456,21 @@ uint64_t oracle_check_scaled(uint64_t seed, uint64_t first, uint64_t count, int 
     if (r1) continue;
     if (oracle_escape_iterations(cre, cim, max_iterations) !=
         oracle_escape_iterations_scaled(cre, cim, max_iterations)) bad++;
+  }
+  return bad;
+}
+
+uint64_t oracle_check_scaled_ship(uint64_t seed, uint64_t first, uint64_t count,
+                                  int max_iterations) {
+  uint64_t bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : bad)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    if (oracle_escape_iterations_ship(cre, cim, max_iterations) !=
+        oracle_escape_iterations_scaled_ship(cre, cim, max_iterations)) bad++;
   }
   return bad;
 }

@@ -69,6 +69,18 @@ int oracle_render(const oracle_dims *d, int max_iterations, int min_iterations, 
                   uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
                   int threads);
 
+/* Same with burning_ship != 0: the RENDER_BURNING_SHIP build of the reference (cudabrot.cu:15-17,
+ * :327-330, :353-356, :397-399): |re|, |im| before every step, no cardioid/bulb test. */
+int oracle_render_ex(const oracle_dims *d, int max_iterations, int min_iterations, uint64_t seed,
+                     uint64_t first, uint64_t count, uint32_t *hist, oracle_counters *counters,
+                     int threads, int burning_ship);
+int oracle_escape_iterations_ship(double c_real, double c_imag, int max_iterations);
+void oracle_classify_ship(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                          int32_t *out_iters);
+int oracle_escape_iterations_scaled_ship(double c_real, double c_imag, int max_iterations);
+uint64_t oracle_check_scaled_ship(uint64_t seed, uint64_t first, uint64_t count,
+                                  int max_iterations);
+
 /* Escape classification only (no histogram): out_iters[k] = IterateMandelbrot result for sample
  * first+k, or -1 if rejected by the cardioid/bulb test. */
 void oracle_classify(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,

@@ -24,10 +24,12 @@ __global__ void ProbeClassify(const double *samples, int n, int max_iterations, 
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   double real = samples[2 * k], imag = samples[2 * k + 1];
+#ifndef RENDER_BURNING_SHIP  /* as in DrawBuddhabrot, cudabrot.cu:397-399 */
   if (InMainCardioid(real, imag) || InOrder2Bulb(real, imag)) {
     out[k] = -1;
     return;
   }
+#endif
   out[k] = IterateMandelbrot(real, imag, max_iterations);
 }
 

@@ -14,6 +14,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 REF_PROBE = os.path.join(REF_DIR, "ref_probe")
+REF_PROBE_SHIP = os.path.join(REF_DIR, "ref_probe_ship")  # built with -DRENDER_BURNING_SHIP
 REF_BINARY = os.path.join(REF_DIR, "cudabrot_ref")
 
 
@@ -59,12 +60,19 @@ def lib():
         L.oracle_rejected.restype = C.c_int
         L.oracle_escape_iterations.argtypes = [C.c_double, C.c_double, C.c_int]
         L.oracle_escape_iterations.restype = C.c_int
+        L.oracle_escape_iterations_ship.argtypes = [C.c_double, C.c_double, C.c_int]
+        L.oracle_escape_iterations_ship.restype = C.c_int
         L.oracle_cycle_detect_iterations.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
         L.oracle_cycle_detect_iterations.restype = C.c_int
         L.oracle_render.argtypes = [C.POINTER(Dims), C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                     C.c_uint64, u32p, C.POINTER(Counters), C.c_int]
         L.oracle_render.restype = C.c_int
+        L.oracle_render_ex.argtypes = L.oracle_render.argtypes + [C.c_int]
+        L.oracle_render_ex.restype = C.c_int
         L.oracle_classify.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, i32p]
+        L.oracle_classify_ship.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, i32p]
+        L.oracle_check_scaled_ship.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+        L.oracle_check_scaled_ship.restype = C.c_uint64
         L.oracle_tonemap.argtypes = [u32p, C.c_size_t, C.c_double, C.c_int, u16p, u32p,
                                      C.POINTER(C.c_double)]
         L.oracle_write_pgm.argtypes = [C.c_char_p, u16p, C.c_int, C.c_int]
@@ -119,20 +127,21 @@ def make_dims(w, h, min_real=-2.0, max_real=2.0, min_imag=-2.0, max_imag=2.0):
 
 
 def render(w, h, max_iter, min_iter, seed, first, count, canvas=(-2.0, 2.0, -2.0, 2.0),
-           hist=None, threads=0):
+           hist=None, threads=0, burning_ship=False):
     """Returns (hist uint32[h,w], counters dict, threads used)."""
     d = make_dims(w, h, *canvas)
     if hist is None:
         hist = np.zeros((h, w), dtype=np.uint32)
     cnt = Counters()
-    nt = lib().oracle_render(C.byref(d), max_iter, min_iter, seed, first, count,
-                             _p(hist, C.c_uint32), C.byref(cnt), threads)
+    nt = lib().oracle_render_ex(C.byref(d), max_iter, min_iter, seed, first, count,
+                                _p(hist, C.c_uint32), C.byref(cnt), threads, int(burning_ship))
     return hist, cnt.as_dict(), nt
 
 
-def classify(seed, first, count, max_iter):
+def classify(seed, first, count, max_iter, burning_ship=False):
     out = np.empty(count, dtype=np.int32)
-    lib().oracle_classify(seed, first, count, max_iter, _p(out, C.c_int32))
+    fn = lib().oracle_classify_ship if burning_ship else lib().oracle_classify
+    fn(seed, first, count, max_iter, _p(out, C.c_int32))
     return out
 
 
@@ -162,9 +171,10 @@ def max_threads():
     return int(lib().oracle_max_threads())
 
 
-def check_scaled(seed, first, count, max_iter):
+def check_scaled(seed, first, count, max_iter, burning_ship=False):
     """Mismatches between the reference-form and the product's scaled recurrence / rejection."""
-    return int(lib().oracle_check_scaled(seed, first, count, max_iter))
+    fn = lib().oracle_check_scaled_ship if burning_ship else lib().oracle_check_scaled
+    return int(fn(seed, first, count, max_iter))
 
 
 def check_fast_bin(dims, points):
@@ -180,6 +190,7 @@ def check_fast_bin(dims, points):
     return int(bad), int(ex.value), int(inc.value)
 
 
-def run_ref_probe(*args):
+def run_ref_probe(*args, burning_ship=False):
     """Run oracle/_ref/ref_probe (the reference's own code, prebuilt); returns CompletedProcess."""
-    return subprocess.run([REF_PROBE] + [str(a) for a in args], capture_output=True, text=True)
+    exe = REF_PROBE_SHIP if burning_ship else REF_PROBE
+    return subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)

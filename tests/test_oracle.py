@@ -85,11 +85,30 @@ def test_quirks(oracle):
             oracle.make_dims(*bad)
 
 
+def test_burning_ship_differs_and_skips_rejection(oracle):
+    """RENDER_BURNING_SHIP (cudabrot.cu:15-17, :397-399): no cardioid/bulb rejection, a different
+    set; the upper-right quadrant start (re, im >= 0 throughout) is NOT enough to make the two
+    variants agree because the orbit leaves the quadrant."""
+    h0, c0, _ = oracle.render(128, 128, 200, 10, 1337, 0, 1 << 16)
+    h1, c1, _ = oracle.render(128, 128, 200, 10, 1337, 0, 1 << 16, burning_ship=True)
+    assert c1["rejected"] == 0 and c0["rejected"] > 0
+    assert c1["candidates"] == c0["candidates"] == 1 << 16
+    assert not np.array_equal(h0, h1)
+    assert c1["accepted"] > 0 and int(h1.sum()) == c1["increments"]
+    # single points: c = -1.45 - 0.1i is inside the ship and escapes after 6 Mandelbrot steps
+    L = oracle.lib()
+    assert L.oracle_escape_iterations_ship(-1.45, -0.1, 5000) == 5000
+    assert L.oracle_escape_iterations(-1.45, -0.1, 5000) == 6
+
+
 def test_scaled_recurrence_is_bit_identical(oracle):
     """The product's 4-instruction scaled step and scaled cardioid/bulb test give the same escape
     index / verdict as the reference dataflow on every sample."""
     assert oracle.check_scaled(1337, 0, 1 << 22, 500) == 0
     assert oracle.check_scaled(42, 1 << 40, 1 << 20, 5000) == 0
+    # the burning-ship variant (|re|, |im| before each step) under the same scaling
+    assert oracle.check_scaled(1337, 0, 1 << 21, 500, burning_ship=True) == 0
+    assert oracle.check_scaled(7, 1 << 35, 1 << 19, 5000, burning_ship=True) == 0
 
 
 CANVASES = [(1000, 1000, (-2.0, 2.0, -2.0, 2.0)), (20000, 20000, (-2.0, 2.0, -2.0, 2.0)),

@@ -14,6 +14,9 @@ COUNTER_KEYS = ["candidates", "rejected", "hit_max", "too_early", "accepted", "e
                 "orbit_points", "increments"]
 
 
+SHIP_CANVAS = (-2.2, 1.8, -2.5, 1.5)   # the ship sits below the real axis (imag grows downward)
+
+
 def gpu_render(buddha, w, h, m, c, seed, first, count, canvas=FULL, flags=0):
     with buddha.Renderer(w, h, m, c, canvas=canvas, seed=seed, flags=flags) as r:
         r.render_samples(first, count)
@@ -94,6 +97,20 @@ def test_tile_binned_scatter_agrees(buddha, oracle, monkeypatch, pool_mb):
             r.render_samples(1000, (1 << 20) - 1000)
             r.render_samples(1 << 20, n - (1 << 20))
             assert_same(r.read_histogram(), r.counters(), ohist, ocnt)
+
+
+@pytest.mark.parametrize("extra", ["", "F_NO_SHORTCUT", "F_SIMPLE_KERNEL", "F_FORCE_TILED"])
+def test_burning_ship_matches_oracle(buddha, oracle, extra):
+    """BUDDHA_F_BURNING_SHIP = the reference built with RENDER_BURNING_SHIP (cudabrot.cu:15-17,
+    :327-330, :353-356, :397-399)."""
+    flags = buddha.F_BURNING_SHIP | (getattr(buddha, extra) if extra else 0)
+    for (w, h, m, c, canvas, n) in [(600, 600, 500, 20, FULL, 1 << 20),
+                                    (512, 384, 20000, 2000, SHIP_CANVAS, 1 << 19),
+                                    (96, 64, 7, 0, FULL, 70001)]:
+        ohist, ocnt, _ = oracle.render(w, h, m, c, 1337, 5, n, canvas=canvas, burning_ship=True)
+        assert ocnt["rejected"] == 0
+        hist, cnt = gpu_render(buddha, w, h, m, c, 1337, 5, n, canvas, flags=flags)
+        assert_same(hist, cnt, ohist, ocnt)
 
 
 def test_shortcut_statistics(buddha):
@@ -216,6 +233,17 @@ def test_reference_device_code_agrees_with_oracle(oracle, tmp_path):
         ref_hist = np.fromfile(hp, dtype=np.uint32).reshape(h, w)
         assert np.array_equal(ref_iters, oracle.classify(1337, first, n, m))
         ohist, _, _ = oracle.render(w, h, m, c, 1337, first, n, canvas=canvas)
+        assert np.array_equal(ref_hist, ohist)
+        # the same harness compiled with -DRENDER_BURNING_SHIP pins the ship variant
+        if not os.path.exists(oracle.REF_PROBE_SHIP):
+            pytest.fail("oracle/_ref/ref_probe_ship missing")
+        r = oracle.run_ref_probe("orbits", w, h, repr(canvas[0]), repr(canvas[1]), repr(canvas[2]),
+                                 repr(canvas[3]), m, c, sp, ip, hp, burning_ship=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ref_iters = np.fromfile(ip, dtype=np.int32)
+        ref_hist = np.fromfile(hp, dtype=np.uint32).reshape(h, w)
+        assert np.array_equal(ref_iters, oracle.classify(1337, first, n, m, burning_ship=True))
+        ohist, _, _ = oracle.render(w, h, m, c, 1337, first, n, canvas=canvas, burning_ship=True)
         assert np.array_equal(ref_hist, ohist)
 
 
