@@ -29,8 +29,10 @@ EXPORTS = [
     "buddha_render_seconds", "buddha_last_render_ms", "buddha_get_counters",
     "buddha_reset_counters", "buddha_tonemap_u16", "buddha_last_tonemap_ms",
     "buddha_device_histogram", "buddha_stream", "buddha_merge", "buddha_probe_fp64_peak",
-    "buddha_probe_red_peak",
+    "buddha_probe_red_peak", "buddha_read_channel", "buddha_tonemap_channel_u16",
+    "buddha_get_channel_counters",
 ]
+MAX_CHANNELS = 4
 
 
 class Params(C.Structure):
@@ -40,7 +42,9 @@ class Params(C.Structure):
                 ("min_real", C.c_double), ("max_real", C.c_double),
                 ("min_imag", C.c_double), ("max_imag", C.c_double),
                 ("max_iterations", C.c_int32), ("min_iterations", C.c_int32),
-                ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_channels", C.c_uint32), ("channel_max", C.c_int32 * 4),
+                ("channel_min", C.c_int32 * 4), ("reserved2", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -110,6 +114,10 @@ def lib():
     L.buddha_get_counters.argtypes = [ctx, C.POINTER(Counters)]
     L.buddha_reset_counters.argtypes = [ctx]
     L.buddha_tonemap_u16.argtypes = [ctx, C.c_double, C.c_int, C.c_void_p, C.c_size_t, u32p, dblp]
+    L.buddha_tonemap_channel_u16.argtypes = [ctx, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                                             C.c_size_t, u32p, dblp]
+    L.buddha_read_channel.argtypes = [ctx, C.c_int, C.c_void_p, C.c_size_t]
+    L.buddha_get_channel_counters.argtypes = [ctx, C.c_int, C.POINTER(Counters)]
     L.buddha_last_tonemap_ms.argtypes = [ctx, C.POINTER(C.c_float)]
     L.buddha_device_histogram.argtypes = [ctx]
     L.buddha_device_histogram.restype = C.c_void_p

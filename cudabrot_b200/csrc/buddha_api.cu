@@ -24,6 +24,7 @@ namespace {
 thread_local char g_create_error[512] = "";
 
 constexpr uint32_t kLutMax = 1u << 22;  // counts below this are tone-mapped through a full table
+constexpr int kTotalCnt = kCntSlots + kMaxChannels * kChSlots;  // common + per-channel accumulators
 
 struct FastBin {
   double inv_half, c0_lo, c0_hi;
@@ -35,9 +36,12 @@ struct FastBin {
 struct buddha_ctx {
   buddha_params params;
   double delta_re, delta_im;
-  size_t cells;
+  size_t cells;                   // all channels
+  size_t ch_cells;                // w * h
+  int n_ch;                       // 1, or the channels of a fused context
   int sm_count;
   int grid;                       // persistent grid: resident CTAs per SM x SMs
+  int variant;                    // kernel instantiation: kVarShip | kVarFused
   cudaStream_t stream;
   cudaEvent_t ev_a, ev_b, ev_ta, ev_tb;
   uint32_t *d_hist;
@@ -123,6 +127,13 @@ void fill_render_params(buddha_ctx *c) {
   r.max_it = p.max_iterations; r.min_it = p.min_iterations;
   r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
   r.ship = (p.flags & BUDDHA_F_BURNING_SHIP) ? 1 : 0;
+  r.n_ch = c->n_ch > 1 ? c->n_ch : 0;
+  r.ch_stride = (uint32_t)c->ch_cells;
+  r.ch_low = p.max_iterations;
+  for (int k = 0; k < c->n_ch && c->n_ch > 1; k++) {
+    r.ch_max[k] = p.channel_max[k]; r.ch_min[k] = p.channel_min[k];
+    r.ch_low = std::min(r.ch_low, p.channel_max[k]);
+  }
   uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
   for (int i = 0; i < 10; i++) {
     r.key0[i] = k0; r.key1[i] = k1;
@@ -263,11 +274,35 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
                 p->device, prop.major, prop.minor);
   CU(nullptr, cudaSetDevice(p->device));
 
+  const int n_ch = p->n_channels > 1 ? (int)p->n_channels : 1;
+  if (n_ch > BUDDHA_MAX_CHANNELS)
+    return fail(nullptr, BUDDHA_EINVAL, "at most %d channels", BUDDHA_MAX_CHANNELS);
+  if (n_ch > 1) {
+    for (int k = 0; k < n_ch; k++)
+      if (p->channel_max[k] <= kT2End || p->channel_max[k] >= (1 << kOrbStepBits))
+        return fail(nullptr, BUDDHA_EINVAL, "channel %d: max iterations must be > %d and < 2^%d", k,
+                    kT2End, kOrbStepBits);
+    if (p->flags & BUDDHA_F_SIMPLE_KERNEL)
+      return fail(nullptr, BUDDHA_EINVAL, "the debug kernel renders one channel only");
+    if ((uint64_t)p->width * (uint64_t)p->height * (uint64_t)n_ch > 0xffffffffull)
+      return fail(nullptr, BUDDHA_EINVAL, "n_channels*width*height exceeds 2^32-1 cells");
+  }
+
   buddha_ctx *c = (buddha_ctx *)calloc(1, sizeof(buddha_ctx));
   if (!c) return fail(nullptr, BUDDHA_ENOMEM, "out of host memory");
   c->params = *p;
+  if (n_ch > 1) {  // the fused pass runs with the widest limits
+    c->params.max_iterations = p->channel_max[0];
+    c->params.min_iterations = p->channel_min[0];
+    for (int k = 1; k < n_ch; k++) {
+      c->params.max_iterations = std::max(c->params.max_iterations, p->channel_max[k]);
+      c->params.min_iterations = std::min(c->params.min_iterations, p->channel_min[k]);
+    }
+  }
   c->delta_re = dre; c->delta_im = dim;
-  c->cells = (size_t)p->width * (size_t)p->height;
+  c->n_ch = n_ch;
+  c->ch_cells = (size_t)p->width * (size_t)p->height;
+  c->cells = c->ch_cells * (size_t)n_ch;
   c->sm_count = prop.multiProcessorCount;
   fill_render_params(c);
 
@@ -275,11 +310,14 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   // the work stacks are dynamic shared memory (110 KB per CTA: opt-in above 48 KB)
   c->render_smem = kQueueBytes;
   if (const char *e = getenv("BUDDHA_PAD_SMEM")) c->smem_pad = (size_t)atoi(e);  // occupancy experiments
-  const bool ship = (p->flags & BUDDHA_F_BURNING_SHIP) != 0;
-  const void *render_fn = ship ? (const void *)render_persistent_kernel<true>
-                               : (const void *)render_persistent_kernel<false>;
+  c->variant = ((p->flags & BUDDHA_F_BURNING_SHIP) ? kVarShip : 0) | (n_ch > 1 ? kVarFused : 0);
+  const void *render_fns[4] = {(const void *)render_persistent_kernel<0>,
+                               (const void *)render_persistent_kernel<1>,
+                               (const void *)render_persistent_kernel<2>,
+                               (const void *)render_persistent_kernel<3>};
+  const void *render_fn = render_fns[c->variant];
   cudaError_t st = cudaFuncSetAttribute(render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(kQueueBytes + c->smem_pad + 8192));
+                                        (int)prop.sharedMemPerBlockOptin);
   if (st == cudaSuccess)
     st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_fn, kThreadsPerCta,
                                                        c->render_smem + c->smem_pad);
@@ -309,8 +347,8 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaMalloc(&c->d_hist, c->cells * sizeof(uint32_t)));
   CUC(cudaMemsetAsync(c->d_hist, 0, c->cells * sizeof(uint32_t), c->stream));
   CUC(cudaMalloc(&c->d_cursor, sizeof(unsigned long long)));
-  CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCntSlots));
-  CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
+  CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kTotalCnt));
+  CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kTotalCnt, c->stream));
   CUC(cudaMalloc(&c->d_max, sizeof(uint32_t)));
   for (int b = 0; b < 2; b++) {
     c->spill[b].capacity = (unsigned)c->grid * kWarpsPerCta * kStackCap;  // every warp spills < kStackCap
@@ -430,6 +468,18 @@ int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
   return BUDDHA_OK;
 }
 
+int buddha_read_channel(buddha_ctx *c, int channel, uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
+  if (cells != c->ch_cells)
+    return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, a channel has %zu", cells, c->ch_cells);
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemcpyAsync(host, c->d_hist + (size_t)channel * c->ch_cells, cells * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
 // One render launch (+ the orbit drain, + the tile apply when tiling is on) for [first, first+count).
 static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   RenderParams rp = c->rp;
@@ -459,12 +509,15 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
     const size_t dyn = c->tiled ? c->tile_smem : 0;
     const size_t rsmem = c->render_smem + c->smem_pad + dyn;
-    if (rp.ship)
-      render_persistent_kernel<true><<<grid, kThreadsPerCta, rsmem, c->stream>>>(
-          rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
-    else
-      render_persistent_kernel<false><<<grid, kThreadsPerCta, rsmem, c->stream>>>(
-          rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
+#define BUDDHA_LAUNCH_VARIANT(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                         \
+  switch (c->variant) {                                                                     \
+    case 0: KERNEL<0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                   \
+    case 1: KERNEL<1><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                   \
+    case 2: KERNEL<2><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                   \
+    default: KERNEL<3><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                  \
+  }
+    BUDDHA_LAUNCH_VARIANT(render_persistent_kernel, grid, kThreadsPerCta, rsmem, c->stream, rp,
+                          c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
     CU(c, cudaGetLastError());
     // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render
     // kernel of the following launch.
@@ -477,12 +530,8 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     // orbits the warps could not run with enough lanes: finished with grid-wide refill
     const int dgrid = (grid * kWarpsPerCta + kDrainWarps - 1) / kDrainWarps;
     const size_t ddyn = c->tiled ? (size_t)c->n_tiles * kDrainWarps * sizeof(uint2) : 0;
-    if (rp.ship)
-      orbit_drain_kernel<true><<<dgrid, kDrainWarps * 32, ddyn, side>>>(
-          rp, c->d_hist, c->d_counters, c->spill[b], c->d_spill_next[b]);
-    else
-      orbit_drain_kernel<false><<<dgrid, kDrainWarps * 32, ddyn, side>>>(
-          rp, c->d_hist, c->d_counters, c->spill[b], c->d_spill_next[b]);
+    BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
+                          c->d_counters, c->spill[b], c->d_spill_next[b]);
     c->launches += 1;
     if (pipelined) {
       // apply this launch's lists while the next launch renders
@@ -641,12 +690,44 @@ int buddha_last_render_ms(buddha_ctx *c, float *ms) {
   return BUDDHA_OK;
 }
 
+static int read_counters(buddha_ctx *c, unsigned long long *v) {
+  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaMemcpyAsync(v, c->d_counters, sizeof(unsigned long long) * kTotalCnt,
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_get_channel_counters(buddha_ctx *c, int channel, buddha_counters *out) {
+  if (!c || !out) return BUDDHA_EINVAL;
+  if (c->n_ch < 2) return channel == 0 ? buddha_get_counters(c, out) : BUDDHA_EINVAL;
+  if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
+  unsigned long long v[kTotalCnt];
+  int rc = read_counters(c, v);
+  if (rc) return rc;
+  const unsigned long long *ch = v + kCntSlots + channel * kChSlots;
+  memset(out, 0, sizeof(*out));
+  out->candidates = c->candidates;
+  out->rejected = v[kCntRejected];
+  out->hit_max = ch[kChHit];
+  out->accepted = ch[kChAccepted];
+  out->too_early = c->candidates - v[kCntRejected] - ch[kChHit] - ch[kChAccepted];
+  // sum over samples of min(steps run, this channel's limit)
+  out->escape_iters = v[kCntEscapeIters] - ch[kChOver];
+  out->orbit_points = ch[kChPoints];
+  out->increments = ch[kChIncrements];
+  out->executed_iters = v[kCntExecuted];
+  out->shortcut_hits = v[kCntShortcut];
+  out->exact_bins = v[kCntExactBins];
+  out->kernel_launches = c->launches;
+  return BUDDHA_OK;
+}
+
 int buddha_get_counters(buddha_ctx *c, buddha_counters *out) {
   if (!c || !out) return BUDDHA_EINVAL;
-  unsigned long long v[kCntSlots];
-  CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemcpyAsync(v, c->d_counters, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  unsigned long long v[kTotalCnt];
+  int rc = read_counters(c, v);
+  if (rc) return rc;
   memset(out, 0, sizeof(*out));
   out->candidates = c->candidates;
   out->rejected = v[kCntRejected];
@@ -667,7 +748,7 @@ int buddha_get_counters(buddha_ctx *c, buddha_counters *out) {
 int buddha_reset_counters(buddha_ctx *c) {
   if (!c) return BUDDHA_EINVAL;
   CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCntSlots, c->stream));
+  CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kTotalCnt, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->candidates = 0;
   c->launches = 0;
@@ -676,16 +757,24 @@ int buddha_reset_counters(buddha_ctx *c) {
 
 int buddha_tonemap_u16(buddha_ctx *c, double gamma, int big_endian, uint16_t *host_out,
                        size_t cells, uint32_t *max_out, double *scale_out) {
+  return buddha_tonemap_channel_u16(c, 0, gamma, big_endian, host_out, cells, max_out, scale_out);
+}
+
+int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big_endian,
+                               uint16_t *host_out, size_t cells, uint32_t *max_out,
+                               double *scale_out) {
   if (!c) return BUDDHA_EINVAL;
-  if (host_out && cells != c->cells)
-    return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->cells);
+  if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
+  if (host_out && cells != c->ch_cells)
+    return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->ch_cells);
+  const uint32_t *d_src = c->d_hist + (size_t)channel * c->ch_cells;
   CU(c, cudaSetDevice(c->params.device));
   const int blocks = c->sm_count * 8;
 
   // pass 1: GetLinearColorScale's maximum (cudabrot.cu:430-435)
   CU(c, cudaEventRecord(c->ev_ta, c->stream));
   CU(c, cudaMemsetAsync(c->d_max, 0, sizeof(uint32_t), c->stream));
-  hist_max_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hist, c->cells, c->d_max);
+  hist_max_kernel<<<blocks, 256, 0, c->stream>>>(d_src, c->ch_cells, c->d_max);
   CU(c, cudaGetLastError());
   c->launches += 1;
   uint32_t mx = 0;
@@ -734,16 +823,16 @@ int buddha_tonemap_u16(buddha_ctx *c, double gamma, int big_endian, uint16_t *ho
     CU(c, cudaMemcpyAsync(c->d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,
                           c->stream));
   }
-  if (!c->d_gray) CU(c, cudaMalloc(&c->d_gray, sizeof(uint16_t) * c->cells));
+  if (!c->d_gray) CU(c, cudaMalloc(&c->d_gray, sizeof(uint16_t) * c->ch_cells));
 
   // pass 2: the map itself, 4 B read + 2 B written per pixel
-  tonemap_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hist, c->d_gray, c->cells, c->d_lut, lut_size,
+  tonemap_kernel<<<blocks, 256, 0, c->stream>>>(d_src, c->d_gray, c->ch_cells, c->d_lut, lut_size,
                                                 c->d_thr, big_endian ? 1 : 0);
   CU(c, cudaGetLastError());
   c->launches += 1;
   CU(c, cudaEventRecord(c->ev_tb, c->stream));
   c->tonemap_timed = true;
-  CU(c, cudaMemcpyAsync(host_out, c->d_gray, sizeof(uint16_t) * c->cells, cudaMemcpyDeviceToHost,
+  CU(c, cudaMemcpyAsync(host_out, c->d_gray, sizeof(uint16_t) * c->ch_cells, cudaMemcpyDeviceToHost,
                         c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return BUDDHA_OK;

@@ -35,6 +35,8 @@ constexpr int kBlock = 16;                     // unchecked steps per deep round
 constexpr int kDeepExit = 24;                  // leave a phase when fewer lanes than this are busy
 constexpr int kOrbExit = 16;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxChannels = 4;                // fused multi-channel render
+constexpr int kOrbStepBits = 28;               // fused: orbit entries carry (mask << 28) | steps
 
 // Fast binning: T = fma(X, inv_half, C0) lands in [1.5*2^40, 1.5*2^40 + 2^20) for in-range
 // quotients, where the low mantissa word holds quotient * 2^12.
@@ -45,6 +47,8 @@ enum CounterSlot {
   kCntRejected = 0, kCntHitMax, kCntTooEarly, kCntAccepted, kCntEscapeIters, kCntOrbitPoints,
   kCntIncrements, kCntExecuted, kCntShortcut, kCntExactBins, kCntSlots
 };
+// fused render: per-channel accumulators follow the kCntSlots common ones, kChSlots per channel
+enum ChannelSlot { kChHit = 0, kChOver, kChAccepted, kChPoints, kChIncrements, kChSlots };
 
 struct RenderParams {
   // canvas in the reference's form (exact binning path), cudabrot.cu:46-58
@@ -57,6 +61,13 @@ struct RenderParams {
   int32_t max_it, min_it;
   int32_t shortcut;
   int32_t ship;                 // burning-ship variant (only the simple kernel reads this at run time)
+  // fused multi-channel render: channel k accepts a sample that escapes at step `it` iff
+  // ch_min[k] <= it - 1 < ch_max[k]; its histogram starts at hist + k * ch_stride.  max_it /
+  // min_it above are then the largest ch_max / the smallest ch_min.
+  int32_t n_ch;
+  int32_t ch_max[kMaxChannels], ch_min[kMaxChannels];
+  int32_t ch_low;               // smallest ch_max: below it no channel has hit its limit yet
+  uint32_t ch_stride;           // cells per channel
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
   // tile-binned scatter for histograms much larger than L2 (0 = off, see scatter())
@@ -87,19 +98,21 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-// One step of z <- z^2 + c on the scaled state (4 FP64 instructions).  kShip: the burning-ship
+// One step of z <- z^2 + c on the scaled state (4 FP64 instructions).  Ship step: the burning-ship
 // variant (RENDER_BURNING_SHIP, cudabrot.cu:15-17, :327-330, :353-356), real = |real|, imag =
 // |imag| before the step -- only the cross term sees the difference, as operand modifiers
 // (the reference's own SASS for that build: DADD |re|,|re|; DFMA r2,|im|,c_im).
-template <bool kShip>
+template <bool kShipStep>
 __device__ __forceinline__ void zstep(double &x, double &y, double cx, double cy) {
   const double a4 = __dmul_rn(y, y);
   const double b4 = __fma_rn(x, x, -a4);
-  const double yn = kShip ? __fma_rn(fabs(x), fabs(y), cy) : __fma_rn(x, y, cy);
+  const double yn = kShipStep ? __fma_rn(fabs(x), fabs(y), cy) : __fma_rn(x, y, cy);
   x = __fma_rn(b4, 0.5, cx);
   y = yn;
 }
-#define BUDDHA_ZSTEP(x, y, cx, cy) zstep<kShip>((x), (y), (cx), (cy))
+// Kernel variants (template parameter kVar): bit 0 = burning ship, bit 1 = fused multi-channel.
+constexpr int kVarShip = 1, kVarFused = 2;
+#define BUDDHA_ZSTEP(x, y, cx, cy) zstep<(kVar & kVarShip) != 0>((x), (y), (cx), (cy))
 
 // 4 * (re^2 + im^2) with the reference's rounding order (cudabrot.cu:336).
 __device__ __forceinline__ double norm4(double x, double y) {
@@ -205,17 +218,25 @@ __device__ __forceinline__ void tile_counters_store(const RenderParams &p, const
 
 // IncrementPixelCounter (cudabrot.cu:302-314) verbatim in arithmetic: IEEE subtract, IEEE divide,
 // cvt.rzi (saturating), 32-bit index.
-__device__ __forceinline__ bool bin_exact(double x2, double y2, const RenderParams &p,
-                                          const Sink &hist) {
+__device__ __forceinline__ bool bin_exact_index(double x2, double y2, const RenderParams &p,
+                                                uint32_t *idx) {
   double re = __dmul_rn(x2, 0.5), im = __dmul_rn(y2, 0.5);
   if ((re < p.min_re) || (im < p.min_im)) return false;
   int col = __double2int_rz(__ddiv_rn(__dsub_rn(re, p.min_re), p.delta_re));
   int row = __double2int_rz(__ddiv_rn(__dsub_rn(im, p.min_im), p.delta_im));
   if ((row >= 0) && (row < p.h) && (col >= 0) && (col < p.w)) {
-    scatter(p, hist, (uint32_t)((row * p.w) + col));
+    *idx = (uint32_t)((row * p.w) + col);
     return true;
   }
   return false;
+}
+
+__device__ __forceinline__ bool bin_exact(double x2, double y2, const RenderParams &p,
+                                          const Sink &hist) {
+  uint32_t idx;
+  if (!bin_exact_index(x2, y2, p, &idx)) return false;
+  scatter(p, hist, idx);
+  return true;
 }
 
 // Division-free binning.  For each axis two roundings of (quotient +- 2^-11) onto a 2^-12 grid are
@@ -371,6 +392,7 @@ struct WarpState {
   uint32_t skipped;    // iterations the periodicity shortcut did not have to run (escape_iters only)
   uint32_t wasted;     // deep rounds that were rolled back (executed only)
   uint32_t p_pts, p_inc;
+  uint32_t ch_inc[kMaxChannels];  // fused render only: increments per channel
 };
 
 // Warp-reduce nine per-lane counters and add them to the global accumulators.  Deliberately not
@@ -400,6 +422,26 @@ __device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 }
 
+// Adds v (summed over the warp) to one per-channel accumulator; called from rare branches only.
+__device__ __forceinline__ void channel_add(unsigned long long *counters, int ch, int slot,
+                                            uint32_t v) {
+  v = __reduce_add_sync(kFull, v);
+  if (lane_id() == 0 && v) atomicAdd(counters + kCntSlots + ch * kChSlots + slot, (unsigned long long)v);
+}
+
+// Fused render: the per-channel increment counters.
+template <int kVar>
+__device__ __forceinline__ void flush_channel_counters(const RenderParams &p, WarpState &ws,
+                                                       unsigned long long *counters) {
+  if constexpr ((kVar & kVarFused) != 0) {
+#pragma unroll
+    for (int k = 0; k < kMaxChannels; k++) {
+      if (k < p.n_ch) channel_add(counters, k, kChIncrements, ws.ch_inc[k]);
+      ws.ch_inc[k] = 0;
+    }
+  }
+}
+
 // Ballot-compacted push of one entry per lane with `pred` set.
 __device__ __forceinline__ int push_slot(int &height, bool pred) {
   unsigned m = __ballot_sync(kFull, pred);
@@ -414,18 +456,68 @@ __device__ __forceinline__ void push_z(ZStack &st, int &height, bool pred, doubl
   if (pred) { st.c[slot] = make_double2(cx, cy); st.z[slot] = make_double2(x, y); st.it[slot] = it; }
 }
 
-__device__ __forceinline__ void push_orbit(WarpQueues &q, WarpState &ws, bool acc, double cx,
-                                           double cy, int n) {
+// Channels (bit k) whose window accepts an escape at step `it` (1-based count, it <= max_it).
+__device__ __forceinline__ unsigned accept_mask(const RenderParams &p, int it) {
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxChannels; k++)
+    if (k < p.n_ch && it - 1 >= p.ch_min[k] && it <= p.ch_max[k]) m |= 1u << k;
+  return m;
+}
+
+// The accept filter (cudabrot.cu:407-408) for lanes whose sample escaped at step `it`, and the
+// push of the accepted ones.  Fused render: a sample is pushed if any channel accepts it; the
+// channel mask travels in the top bits of the step count.
+template <int kVar>
+__device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                           unsigned long long *counters, bool esc, double cx,
+                                           double cy, int it) {
+  unsigned mask = 0;
+  bool acc;
+  if constexpr ((kVar & kVarFused) != 0) {
+    mask = esc ? accept_mask(p, it) : 0u;
+    acc = mask != 0u;
+  } else {
+    acc = esc && it - 1 >= p.min_it;
+  }
   if (__ballot_sync(kFull, acc) == 0u) return;
   ws.n_acc += acc ? 1u : 0u;
-  ws.p_pts += acc ? (uint32_t)n : 0u;
+  ws.p_pts += acc ? (uint32_t)it : 0u;
+  int n = it;
+  if constexpr ((kVar & kVarFused) != 0) {
+    for (int k = 0; k < p.n_ch; k++) {
+      const bool a = (mask >> k) & 1u;
+      channel_add(counters, k, kChAccepted, a ? 1u : 0u);
+      channel_add(counters, k, kChPoints, a ? (uint32_t)it : 0u);
+    }
+    n |= (int)(mask << kOrbStepBits);
+  }
   push_z(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
+}
+
+// Fused render: a sample has finished its escape test -- it escaped at step it_f, or (hit) it never
+// escaped within max_it.  Channels whose limit lies below that count it as "hit max" and must not
+// be charged the iterations beyond their limit (escape_iters_k = sum of min(it_f, ch_max[k])).
+template <int kVar>
+__device__ __forceinline__ void channel_finish(const RenderParams &p, unsigned long long *counters,
+                                               bool esc, bool hit, int it_f) {
+  if constexpr ((kVar & kVarFused) != 0) {
+    const bool any = hit || (esc && it_f > p.ch_low);
+    if (__ballot_sync(kFull, any) == 0u) return;
+    const int reached = hit ? p.max_it : it_f;
+    for (int k = 0; k < p.n_ch; k++) {
+      const bool over = any && reached > p.ch_max[k];
+      const bool h = over || (hit && reached >= p.ch_max[k]);  // the largest channel on a true hit
+      channel_add(counters, k, kChHit, h ? 1u : 0u);
+      channel_add(counters, k, kChOver, over ? (uint32_t)(reached - p.ch_max[k]) : 0u);
+    }
+  }
 }
 
 // N steps with the exact per-step escape test (cudabrot.cu:331-338) for all lanes at once.
 // *cnt = steps a lane ran while it had not escaped (the escaping step included); `alive` on
 // return: never escaped.  A step limit below N is applied by the caller afterwards.
-template <bool kShip, int N>
+template <int kVar, int N>
 __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, double cy,
                                              bool &alive, int &cnt) {
 #pragma unroll
@@ -439,7 +531,7 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
 
 // (a) sampler + steps 1..kGenSteps (= 2).  One batch = one candidate per lane.  kCommon: max_it >
 // kGenSteps, so both steps count and survivors move on; otherwise the general limit logic runs.
-template <bool kShip, bool kCommon>
+template <int kVar, bool kCommon>
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
                                           unsigned long long *counters) {
@@ -452,6 +544,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     if (ws.chunk_off >= ws.chunk_len) {
       if (ws.exhausted) break;
       flush_counters(ws, counters);
+      flush_channel_counters<kVar>(p, ws, counters);
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
       base = __shfl_sync(kFull, base, 0);
@@ -466,7 +559,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     uint4 r = philox4x32_10(ws.chunk_base + o, p);
     const double cx = coord2_from_words(r.x, r.y);
     const double cy = coord2_from_words(r.z, r.w);
-    const bool rej = kShip ? false : rejected2(cx, cy);  // cudabrot.cu:397-399
+    const bool rej = (kVar & kVarShip) ? false : rejected2(cx, cy);  // cudabrot.cu:397-399
     const bool cand = valid && !rej;
     ws.n_rej += (valid && rej) ? 1u : 0u;
     double x = cx, y = cy;
@@ -479,14 +572,14 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
       ws.steps += in1 ? 1u : 0u;
       int slot = push_slot(ws.t1_n, in2);
       if (in2) q.t1.c[slot] = make_double2(cx, cy);
-      if (may_accept) push_orbit(q, ws, cand && !in2 && ((in1 ? 1 : 0) >= p.min_it), cx, cy, in1 ? 2 : 1);
+      if (may_accept) push_orbit<kVar>(p, q, ws, counters, cand && !in2, cx, cy, in1 ? 2 : 1);
     } else {
       // max_it <= 2: escapes after the limit do not count; whoever is left has hit max
       const int cnt = in1 ? 2 : 1;  // steps until the escape (if any)
       const bool esc = cand && !in2 && cnt <= allowed;
       ws.steps += cand ? (uint32_t)min(cnt, allowed) : 0u;
       ws.n_hit += (cand && !esc) ? 1u : 0u;
-      if (may_accept) push_orbit(q, ws, esc && (cnt - 1 >= p.min_it), cx, cy, cnt);
+      if (may_accept) push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, cnt);
     }
   }
   __syncwarp();
@@ -508,9 +601,10 @@ __device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pre
 // (b) one tier of the escape test: pops up to 32 candidates that survived A steps, re-computes
 // those steps from c (no tests needed: they are known not to escape), runs steps A+1..A+N with the
 // per-step test.  kToLate = false: survivors go to t2 as c only; true: to `late` with their state.
-template <bool kShip, int A, int N, bool kToLate>
+template <int kVar, int A, int N, bool kToLate>
 __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                           CStack &src, int &src_n) {
+                                           CStack &src, int &src_n,
+                                           unsigned long long *counters) {
   const int take = min(src_n, 32);
   const bool act = (int)lane_id() < take;
   src_n -= take;
@@ -522,7 +616,7 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
   for (int k = 0; k < A; k++) BUDDHA_ZSTEP(x, y, cx, cy);
   bool alive = act;
   int cnt = 0;
-  tested_steps<kShip, N>(x, y, cx, cy, alive, cnt);
+  tested_steps<kVar, N>(x, y, cx, cy, alive, cnt);
   if (p.max_it > A + N) {
     // the common case: every step counts, survivors move on
     ws.steps += (uint32_t)cnt;
@@ -532,15 +626,14 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
       int slot = push_slot(ws.t2_n, alive);
       if (alive) q.t2.c[slot] = make_double2(cx, cy);
     }
-    if (A + N - 1 >= p.min_it)
-      push_orbit(q, ws, act && !alive && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
+    if (A + N - 1 >= p.min_it) push_orbit<kVar>(p, q, ws, counters, act && !alive, cx, cy, A + cnt);
   } else {
     // max_it falls inside this tier: escapes after the limit do not count, the rest has hit max
     const int allowed = p.max_it - A;  // >= 1: nothing is pushed here once max is reached
     const bool esc = act && !alive && cnt <= allowed;
     ws.steps += (uint32_t)min(cnt, allowed);
     ws.n_hit += (act && !esc) ? 1u : 0u;
-    if (A + N - 1 >= p.min_it) push_orbit(q, ws, esc && (A + cnt - 1 >= p.min_it), cx, cy, A + cnt);
+    if (A + N - 1 >= p.min_it) push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, A + cnt);
   }
   __syncwarp();
 }
@@ -548,8 +641,9 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
 // (b') 16 per-step-tested steps from a stored state.  Entries: tier-2 survivors (it = 14), samples
 // handed back by deep (certain to escape within kBlock steps), tails (fewer than kBlock steps left
 // below max), samples that deep cannot take (|c| too close to 2, or deep full right now).
-template <bool kShip>
-__device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q, WarpState &ws) {
+template <int kVar>
+__device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                           unsigned long long *counters) {
   const int take = min(ws.late_n, 32);
   const bool act = (int)lane_id() < take;
   ws.late_n -= take;
@@ -564,7 +658,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   const bool deep_room = ws.deep_n < 32;
   bool alive = act;
   int cnt = 0;
-  tested_steps<kShip, kLateSteps>(x, y, cx, cy, alive, cnt);
+  tested_steps<kVar, kLateSteps>(x, y, cx, cy, alive, cnt);
   const int allowed = min(kLateSteps, p.max_it - it);  // >= 1 for every stored entry
   const bool esc = act && !alive && cnt <= allowed;
   ws.steps += act ? (uint32_t)min(cnt, allowed) : 0u;
@@ -572,7 +666,8 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   const int nit = it + kLateSteps;
   const bool hit = surv && nit >= p.max_it;  // ran all max iterations (allowed == max - it)
   ws.n_hit += hit ? 1u : 0u;
-  push_orbit(q, ws, esc && (it + cnt - 1 >= p.min_it), cx, cy, it + cnt);
+  push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, it + cnt);
+  channel_finish<kVar>(p, counters, esc, hit, it + cnt);
   const bool cont = surv && !hit;
   if (__ballot_sync(kFull, cont)) {
     // deep's no-re-entry argument needs |c| <= 1.99937, and a full unchecked round must fit
@@ -598,9 +693,9 @@ __device__ __forceinline__ bool checkpoint_age(unsigned age) {
 // |c| <= 2 here, an orbit that leaves the radius-2 disc cannot re-enter it,
 // so "escaped somewhere in the round" <=> "outside at the end of the round".  A state that
 // repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (exact shortcut).
-template <bool kShip>
+template <int kVar>
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                           bool drain) {
+                                           bool drain, unsigned long long *counters) {
   const int max_it = p.max_it;
   const bool shortcut = p.shortcut != 0;
   bool act = false;
@@ -661,6 +756,7 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       ws.skipped += hit ? (uint32_t)(max_it - it) : 0u;
       ws.n_hit += hit ? 1u : 0u;
       ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
+      channel_finish<kVar>(p, counters, false, hit, max_it);
       if (__ballot_sync(kFull, back)) push_z(q.late, ws.late_n, back, cx, cy, x, y, it);
       if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
     }
@@ -684,6 +780,9 @@ struct OrbitLane {
 // One recorded step.  The common path is branch-free (the increment is a predicated reduction), so
 // the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
 // the rare exact-binning case branches.
+// (fused render: o.n carries the channel mask above bit kOrbStepBits; the point goes to every
+// accepting channel's histogram)
+template <int kVar>
 __device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane &o, WarpState &ws,
                                           const Sink &hist) {
   // division-free binning, see bin_point
@@ -702,24 +801,41 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane
   const bool fast = o.act && p.fast_bin != 0;
   const bool hit = fast && inrange && same && col < (uint32_t)p.w && row < (uint32_t)p.h;
   const bool slow = o.act && (p.fast_bin == 0 || (inrange && !same));
-  if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
-  ws.p_inc += hit ? 1u : 0u;
-  if (slow) {
-    ws.n_exact += 1u;
-    ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
+  if constexpr ((kVar & kVarFused) != 0) {
+    uint32_t idx = row * (uint32_t)p.w + col;
+    bool in = hit;
+    if (slow) {
+      ws.n_exact += 1u;
+      in = bin_exact_index(o.x, o.y, p, &idx);
+    }
+    const unsigned mask = (unsigned)o.n >> kOrbStepBits;
+    ws.p_inc += in ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < kMaxChannels; k++) {
+      const bool a = in && ((mask >> k) & 1u);
+      if (a) scatter(p, hist, idx + (uint32_t)k * p.ch_stride);
+      ws.ch_inc[k] += a ? 1u : 0u;
+    }
+  } else {
+    if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
+    ws.p_inc += hit ? 1u : 0u;
+    if (slow) {
+      ws.n_exact += 1u;
+      ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
+    }
   }
 }
 
-template <bool kShip>
+template <int kVar>
 __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                            const Sink &hist) {
   BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
-  orbit_bin(p, o, ws, hist);
+  orbit_bin<kVar>(p, o, ws, hist);
   o.n -= o.act ? 1 : 0;
-  o.act = o.act && o.n != 0;
+  o.act = o.act && ((kVar & kVarFused) ? (o.n & ((1 << kOrbStepBits) - 1)) : o.n) != 0;
 }
 
-template <bool kShip>
+template <int kVar>
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                             const Sink &hist) {
   OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
@@ -739,8 +855,8 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     }
     unsigned am = __ballot_sync(kFull, o.act);
     if (__popc(am) < kOrbExit) break;
-    orbit_step<kShip>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
-    orbit_step<kShip>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
+    orbit_step<kVar>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
+    orbit_step<kVar>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
   if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
@@ -758,7 +874,7 @@ struct OrbitSpill {
 // Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles list entries per warp.
 constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 
-template <bool kShip>
+template <int kVar>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSm)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
@@ -776,6 +892,8 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   ws.exhausted = false;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] = 0;
 
 #pragma unroll 1
   for (;;) {
@@ -785,18 +903,18 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     const bool dry = ws.exhausted && ws.chunk_off >= ws.chunk_len;
     const bool dry1 = dry && ws.t1_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
     if (ws.orb_n >= 32) {
-      orbit_phase<kShip>(p, q, ws, sink);
+      orbit_phase<kVar>(p, q, ws, sink);
     } else if (ws.late_n >= 32 || (dry2 && ws.late_n > 0)) {
-      late_phase<kShip>(p, q, ws);
+      late_phase<kVar>(p, q, ws, counters);
     } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
-      deep_phase<kShip>(p, q, ws, dry3);
+      deep_phase<kVar>(p, q, ws, dry3, counters);
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
-      tier_phase<kShip, kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n);
+      tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n, counters);
     } else if (ws.t1_n >= 32 || (dry && ws.t1_n > 0)) {
-      tier_phase<kShip, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n);
+      tier_phase<kVar, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n, counters);
     } else if (!dry) {
-      if (p.max_it > kGenSteps) gen_phase<kShip, true>(p, q, ws, cursor, counters);
-      else gen_phase<kShip, false>(p, q, ws, cursor, counters);
+      if (p.max_it > kGenSteps) gen_phase<kVar, true>(p, q, ws, cursor, counters);
+      else gen_phase<kVar, false>(p, q, ws, cursor, counters);
     } else {
       break;
     }
@@ -816,6 +934,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
+  flush_channel_counters<kVar>(p, ws, counters);
 }
 
 // Finishes the spilled orbits.  The leftovers are few but up to max_it steps long, so their cost is
@@ -830,7 +949,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
 // kernel (tiling).
 constexpr int kDrainWarps = 4;
 
-template <bool kShip>
+template <int kVar>
 __global__ void __launch_bounds__(kDrainWarps * 32)
 orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
                    unsigned long long *__restrict__ counters, OrbitSpill spill,
@@ -844,6 +963,8 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   WarpState ws;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] = 0;
 
   int g = 32;
   {
@@ -856,6 +977,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   const int sub = lane & (g - 1), leader = lane & ~(g - 1);
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
   int n = 0;          // steps this group's orbit still has to record (group-uniform)
+  unsigned mask = 0;  // fused render: the channels that accepted it
   bool more = true;   // the list may still hold entries (group-uniform)
 #pragma unroll 1
   for (;;) {
@@ -870,23 +992,25 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
         if (idx < total) {
           const double4 e = spill.entries[idx];
           cx = e.x; cy = e.y; x = e.z; y = e.w; n = spill.steps[idx];
+          if constexpr ((kVar & kVarFused) != 0) { mask = (unsigned)n >> kOrbStepBits; n &= (1 << kOrbStepBits) - 1; }
         } else {
           more = false;
         }
       }
     }
     if (__ballot_sync(kFull, n > 0) == 0u) break;
-    OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, 1};
+    OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, (int)(mask << kOrbStepBits) | 1};
 #pragma unroll 1
     for (int k = 0; k < g; k++) {
       BUDDHA_ZSTEP(x, y, cx, cy);
       if (sub == k) { o.x = x; o.y = y; }
     }
-    orbit_bin(p, o, ws, sink);
+    orbit_bin<kVar>(p, o, ws, sink);
     n -= g;
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
+  flush_channel_counters<kVar>(p, ws, counters);
 }
 
 // Applies the lists of ONE tile: warp w owns list (t, w).  One launch per tile keeps every
@@ -923,7 +1047,7 @@ hist_max_kernel(const uint32_t *__restrict__ hist, size_t cells, uint32_t *__res
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   uint32_t m = 0;
-  size_t vec = cells / 4;
+  size_t vec = ((size_t)hist & 15) ? 0 : cells / 4;  // (an odd-sized channel of a fused context)
   const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
   for (size_t k = i; k < vec; k += stride) {
     uint4 v = __ldg(h4 + k);
@@ -957,7 +1081,7 @@ tonemap_kernel(const uint32_t *__restrict__ hist, uint16_t *__restrict__ out, si
                const uint32_t *__restrict__ thr, int swap) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t vec = cells / 4;
+  size_t vec = ((size_t)hist & 15) ? 0 : cells / 4;
   const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
   uint2 *o4 = reinterpret_cast<uint2 *>(out);
   for (size_t k = i; k < vec; k += stride) {

@@ -13,9 +13,12 @@ from . import capi
 
 class Renderer:
     def __init__(self, width=1000, height=1000, max_iterations=100, min_iterations=20,
-                 canvas=(-2.0, 2.0, -2.0, 2.0), seed=1337, device=0, flags=0):
+                 canvas=(-2.0, 2.0, -2.0, 2.0), seed=1337, device=0, flags=0, channels=None):
         """canvas = (min_real, max_real, min_imag, max_imag).  Defaults = the reference's defaults
-        (cudabrot.cu:763-772, :530-543)."""
+        (cudabrot.cu:763-772, :530-543).  channels = [(max_iterations, min_iterations), ...] (2..4
+        entries) makes a fused multi-channel context: every candidate is rendered once into each
+        channel whose window accepts it (what generate_hires_color_image.sh:27-59 does with one
+        run of the reference per channel)."""
         self._lib = capi.lib()
         p = capi.default_params()
         p.device = device
@@ -23,9 +26,15 @@ class Renderer:
         p.min_real, p.max_real, p.min_imag, p.max_imag = canvas
         p.max_iterations, p.min_iterations = max_iterations, min_iterations
         p.seed, p.flags = seed, flags
+        self.channels = list(channels) if channels else None
+        if self.channels:
+            p.n_channels = len(self.channels)
+            for k, (m, c) in enumerate(self.channels[:capi.MAX_CHANNELS]):
+                p.channel_max[k], p.channel_min[k] = m, c
+        self.n_channels = len(self.channels) if self.channels else 1
         self.params = p
         self.width, self.height = width, height
-        self.cells = width * height
+        self.cells = width * height * self.n_channels
         self._ctx = C.c_void_p()
         rc = self._lib.buddha_create(C.byref(self._ctx), C.byref(p))
         if rc:
@@ -61,9 +70,17 @@ class Renderer:
         self._check(self._lib.buddha_load_histogram(self._ctx, h.ctypes.data, h.size))
 
     def read_histogram(self, out=None):
+        """uint32[h, w]; fused contexts: uint32[n_channels, h, w]."""
+        if out is None:
+            shape = (self.height, self.width)
+            out = np.empty(((self.n_channels,) + shape) if self.channels else shape, dtype=np.uint32)
+        self._check(self._lib.buddha_read_histogram(self._ctx, out.ctypes.data, out.size))
+        return out
+
+    def read_channel(self, channel, out=None):
         if out is None:
             out = np.empty((self.height, self.width), dtype=np.uint32)
-        self._check(self._lib.buddha_read_histogram(self._ctx, out.ctypes.data, out.size))
+        self._check(self._lib.buddha_read_channel(self._ctx, channel, out.ctypes.data, out.size))
         return out
 
     # -- render (cudabrot.cu:379-414, :483-492) -----------------------------------------------
@@ -92,11 +109,16 @@ class Renderer:
         self._check(self._lib.buddha_get_counters(self._ctx, C.byref(c)))
         return c.as_dict()
 
+    def channel_counters(self, channel):
+        c = capi.Counters()
+        self._check(self._lib.buddha_get_channel_counters(self._ctx, channel, C.byref(c)))
+        return c.as_dict()
+
     def reset_counters(self):
         self._check(self._lib.buddha_reset_counters(self._ctx))
 
     # -- tone-map (cudabrot.cu:416-468, :566-570) ----------------------------------------------
-    def tonemap(self, gamma=1.0, big_endian=False, out=None, want_image=True):
+    def tonemap(self, gamma=1.0, big_endian=False, out=None, want_image=True, channel=0):
         """Returns (uint16 image or None, max, scale)."""
         mx, sc = C.c_uint32(), C.c_double()
         ptr, n = None, 0
@@ -104,8 +126,9 @@ class Renderer:
             if out is None:
                 out = np.empty((self.height, self.width), dtype=np.uint16)
             ptr, n = out.ctypes.data, out.size
-        self._check(self._lib.buddha_tonemap_u16(self._ctx, gamma, int(big_endian), ptr, n,
-                                                 C.byref(mx), C.byref(sc)))
+        self._check(self._lib.buddha_tonemap_channel_u16(self._ctx, channel, gamma,
+                                                         int(big_endian), ptr, n, C.byref(mx),
+                                                         C.byref(sc)))
         return (out if want_image else None), mx.value, sc.value
 
     def last_tonemap_ms(self):

@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-#define BUDDHA_ABI_VERSION 1
+#define BUDDHA_ABI_VERSION 2
+#define BUDDHA_MAX_CHANNELS 4
 
 enum {
   BUDDHA_OK = 0,
@@ -55,6 +56,17 @@ typedef struct {
   uint64_t seed;            /* DEFAULT_RNG_SEED = 1337 in the reference */
   uint32_t flags;
   uint32_t reserved;
+  /* Fused multi-channel render (no reference equivalent: generate_hires_color_image.sh:27-59 runs
+   * the reference once per colour channel).  n_channels >= 2 renders every candidate ONCE and adds
+   * its orbit to each channel k whose window channel_min[k] <= i < channel_max[k] accepts it;
+   * max_iterations / min_iterations above are then ignored.  The histogram becomes
+   * uint32[n_channels][h][w]; channel k is bit-identical to what a single-channel context with
+   * (-m channel_max[k], -c channel_min[k]) renders from the same sample indices.  Every
+   * channel_max must be > 14 and < 2^28.  0 or 1 = the plain single-channel render. */
+  uint32_t n_channels;
+  int32_t channel_max[BUDDHA_MAX_CHANNELS];
+  int32_t channel_min[BUDDHA_MAX_CHANNELS];
+  uint32_t reserved2;
 } buddha_params;
 
 /* Work counters, accumulated over every render call since create / reset_counters.
@@ -104,8 +116,11 @@ int buddha_clear_histogram(buddha_ctx *ctx);
 /* H2D copy of a -s file's content (cudabrot.cu:256-257).  cells must equal w*h. */
 int buddha_load_histogram(buddha_ctx *ctx, const uint32_t *host, size_t cells);
 
-/* D2H copy of the histogram (cudabrot.cu:496-497); row-major uint32[h][w], row 0 = min_imag. */
+/* D2H copy of the histogram (cudabrot.cu:496-497); row-major uint32[h][w], row 0 = min_imag.
+ * Fused contexts: cells = n_channels*w*h for load/read (channel-major); buddha_read_channel copies
+ * one channel (cells = w*h), i.e. exactly one -s file of the reference. */
 int buddha_read_histogram(buddha_ctx *ctx, uint32_t *host, size_t cells);
+int buddha_read_channel(buddha_ctx *ctx, int channel, uint32_t *host, size_t cells);
 
 /* The pass loop + DrawBuddhabrot (cudabrot.cu:483-492, :379-414), reproducible form: renders
  * exactly the candidates with sample indices [first, first+count) into the histogram and returns
@@ -128,6 +143,12 @@ int buddha_render_seconds(buddha_ctx *ctx, double seconds, volatile int *stop, u
 int buddha_last_render_ms(buddha_ctx *ctx, float *ms);
 
 int buddha_get_counters(buddha_ctx *ctx, buddha_counters *out);
+/* Fused contexts: the counters a single-channel render with channel k's limits would report
+ * (candidates, rejected, hit_max, too_early, accepted, escape_iters, orbit_points, increments);
+ * executed_iters, shortcut_hits, exact_bins and kernel_launches are those of the fused pass.
+ * buddha_get_counters itself then describes the fused pass: limits = the widest channel,
+ * accepted = samples accepted by at least one channel, increments = cells hit, once per point. */
+int buddha_get_channel_counters(buddha_ctx *ctx, int channel, buddha_counters *out);
 int buddha_reset_counters(buddha_ctx *ctx);
 
 /* SetGrayscalePixels (cudabrot.cu:454-468 with :425-439, :443-449, :416-420) and, when big_endian
@@ -137,6 +158,12 @@ int buddha_reset_counters(buddha_ctx *ctx);
  * included (the count->grey map is tabulated on the host with the reference's expression). */
 int buddha_tonemap_u16(buddha_ctx *ctx, double gamma, int big_endian, uint16_t *host_out,
                        size_t cells, uint32_t *max_out, double *scale_out);
+
+/* Same for one channel of a fused context (channel 0 of a plain one): each channel is scaled by
+ * its own maximum, as three separate runs of the reference would. */
+int buddha_tonemap_channel_u16(buddha_ctx *ctx, int channel, double gamma, int big_endian,
+                               uint16_t *host_out, size_t cells, uint32_t *max_out,
+                               double *scale_out);
 
 /* Device time of the most recent tone-map kernels (max-reduce + map), in ms. */
 int buddha_last_tonemap_ms(buddha_ctx *ctx, float *ms);

@@ -113,6 +113,48 @@ def test_burning_ship_matches_oracle(buddha, oracle, extra):
         assert_same(hist, cnt, ohist, ocnt)
 
 
+FUSED_CASES = [
+    # (w, h, canvas, channels [(max, min)], samples, flags)
+    (500, 400, FULL, [(100, 20), (1000, 20), (20000, 20)], 1 << 21, ""),       # config 5's trio
+    (333, 77, (-1.7, 0.3, -0.123, 0.777), [(3000, 50), (15, 0), (400, 399)], 300007, ""),
+    (256, 256, FULL, [(60, 30), (2000, 1000)], 1 << 20, "F_NO_SHORTCUT"),      # disjoint windows
+    (700, 500, FULL, [(300, 10), (5000, 100), (40, 5), (17, 16)], (1 << 21) + 5, "F_FORCE_TILED"),
+    (300, 300, SHIP_CANVAS, [(200, 10), (5000, 200)], 1 << 19, "F_BURNING_SHIP"),
+]
+
+
+@pytest.mark.parametrize("case", range(len(FUSED_CASES)))
+def test_fused_channels_match_separate_oracle_runs(buddha, oracle, case):
+    """A fused multi-channel context renders every candidate once; each channel must be
+    bit-identical -- histogram and counters -- to a separate single-channel render with that
+    channel's (-m, -c) over the same sample indices (three runs of the reference in
+    generate_hires_color_image.sh:27-59)."""
+    w, h, canvas, channels, n, fl = FUSED_CASES[case]
+    flags = getattr(buddha, fl) if fl else 0
+    ship = fl == "F_BURNING_SHIP"
+    first = 12345
+    with buddha.Renderer(w, h, canvas=canvas, seed=99, flags=flags, channels=channels) as r:
+        r.render_samples(first, 1000)
+        r.render_samples(first + 1000, n - 1000)
+        full = r.read_histogram()
+        assert full.shape == (len(channels), h, w)
+        for k, (m, c) in enumerate(channels):
+            ohist, ocnt, _ = oracle.render(w, h, m, c, 99, first, n, canvas=canvas,
+                                           burning_ship=ship)
+            assert_same(r.read_channel(k), r.channel_counters(k), ohist, ocnt)
+            assert np.array_equal(full[k], ohist)
+            img, mx, scale = r.tonemap(2.2, big_endian=True, channel=k)
+            oimg, omx, oscale = oracle.tonemap(ohist, 2.2, big_endian=True)
+            assert (mx, scale) == (omx, oscale) and np.array_equal(img, oimg)
+
+
+def test_fused_rejects_bad_channels(buddha):
+    with pytest.raises(buddha.capi.BuddhaError):
+        buddha.Renderer(64, 64, channels=[(100, 20), (14, 0)])       # max must exceed the tiers
+    with pytest.raises(buddha.capi.BuddhaError):
+        buddha.Renderer(64, 64, channels=[(100, 20)] * 5)
+
+
 def test_shortcut_statistics(buddha):
     with buddha.Renderer(256, 256, 20000, 10000) as r:
         r.render_samples(0, 1 << 22)
