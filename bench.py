@@ -40,7 +40,11 @@ WORKLOADS = {
     "cfg5a": (10000, 10000, 100, 20, FULL, 1 << 32),
     "cfg5b": (10000, 10000, 1000, 20, FULL, 1 << 32),
     "cfg5c": (10000, 10000, 20000, 20, FULL, 1 << 32),
+    # config 5 as ONE fused pass: every candidate is rendered once into the three channels
+    "cfg5": (10000, 10000, 20000, 20, FULL, 1 << 32),
 }
+# fused multi-channel workloads: [(max-iter, min-cutoff)] per channel (BASELINE.json configs[4])
+CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)]}
 REFERENCE_PASS = 13107200  # 512 blocks * 512 threads * 50 samples, cudabrot.cu:20,23,34
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_persistent_kernel launch over 2^30
 # samples, from the `ncu --set full` captures summarised in profiles/r01_summary.md
@@ -108,9 +112,18 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def time_cpu_oracle(wl, budget_s=12.0):
-    """cpu_baseline: the OpenMP oracle on this host's cores, on a bounded sample of the workload."""
+def time_cpu_oracle(wl, budget_s=12.0, channels=None):
+    """cpu_baseline: the OpenMP oracle on this host's cores, on a bounded sample of the workload.
+    Multi-channel workloads: one oracle run per channel, as the reference is used
+    (generate_hires_color_image.sh:27-59); the rate is samples / total time."""
     import oracle_lib as O
+    if channels:
+        parts = [time_cpu_oracle((wl[0], wl[1], m, c, wl[4], wl[5]), budget_s / len(channels))
+                 for (m, c) in channels]
+        return {"value": 1.0 / sum(1.0 / p["value"] for p in parts), "unit": "samples/s",
+                "cores": parts[0]["cores"], "kind": "port",
+                "sample": "one run per channel: " + "; ".join(p["sample"] for p in parts),
+                "orbit_points_per_s": None}
     w, h, m, c, canvas, _ = wl
     n, dt = 1 << 22, 0.0
     for _ in range(3):  # grow the sample until it is worth ~budget_s of CPU work
@@ -213,8 +226,11 @@ def native_arm(args, wl, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     flags = B.F_NO_SHORTCUT if args.no_shortcut else 0
-    r = B.Renderer(w, h, m, c, canvas=canvas, seed=1337, device=local_rank, flags=flags)
-    cells = w * h
+    channels = CHANNELS.get(args.workload)
+    r = B.Renderer(w, h, m, c, canvas=canvas, seed=1337, device=local_rank, flags=flags,
+                   channels=channels)
+    n_ch = len(channels) if channels else 1
+    cells = w * h * n_ch
     hist_t = r.histogram_as_tensor()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -262,6 +278,10 @@ def native_arm(args, wl, rank, world, local_rank):
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     clocks = sampler.stop() if rank == 0 else None
     cnt = r.counters()
+    # cells incremented: fused contexts add a point to every accepting channel
+    inc_local = sum(r.channel_counters(k)["increments"] for k in range(n_ch)) if channels \
+        else cnt["increments"]
+    increments_total = inc_local
 
     total_ms = dev_ms + merge_ms
     if world > 1:
@@ -274,14 +294,17 @@ def native_arm(args, wl, rank, world, local_rank):
         dist.all_reduce(ct, op=dist.ReduceOp.SUM)
         for k, v in zip(keys, ct.tolist()):
             cnt[k] = v
+        it = torch.tensor([inc_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        increments_total = int(it[0])
     samples_total = per_gpu * args.steps * world
     value = samples_total / (total_ms * 1e-3)
 
     # sanity: the merged histogram holds exactly the increments all ranks counted
     if rank == 0:
         merged_sum = int(hist_t.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum())
-        if merged_sum != cnt["increments"]:
-            raise RuntimeError("histogram sum %d != increments %d" % (merged_sum, cnt["increments"]))
+        if merged_sum != increments_total:
+            raise RuntimeError("histogram sum %d != increments %d" % (merged_sum, increments_total))
 
     # ---- e2e: the same steps through the C ABI with HOST buffers ---------------------------
     # per step: H2D of the in-progress histogram (the -s buffer, cudabrot.cu:256), render, D2H of
@@ -294,8 +317,9 @@ def native_arm(args, wl, rank, world, local_rank):
         f, n = step_range(k, rank, world, per_gpu, first=1 << 57)
         r.load_histogram(host_hist)
         r.render_samples(f, n)
-        r.read_histogram(host_hist.reshape(h, w))
-        r.tonemap(1.0, True, out=host_img.reshape(h, w))
+        r.read_histogram(host_hist.reshape((n_ch, h, w) if channels else (h, w)))
+        for ch in range(n_ch):
+            r.tonemap(1.0, True, out=host_img.reshape(n_ch, h, w)[ch], channel=ch)
     barrier()
     e2e_s = time.perf_counter() - e2e_t0
     if world > 1:
@@ -348,9 +372,11 @@ def native_arm(args, wl, rank, world, local_rank):
                    "l2": "256 MiB flush write between timed steps",
                    "parallelism": "%d x disjoint Philox ranges%s" %
                    (world, " + 1 ncclReduce(sum) at the end (timed)" if world > 1 else ""),
-                   "shortcut": not args.no_shortcut},
+                   "shortcut": not args.no_shortcut,
+                   **({"channels": channels, "fused": "one pass feeds all channels"}
+                      if channels else {})},
         "orbit_points_per_s": cnt["orbit_points"] / (total_ms * 1e-3),
-        "increments_per_s": cnt["increments"] / (total_ms * 1e-3),
+        "increments_per_s": increments_total / (total_ms * 1e-3),
         "wall_ms_per_step": wall_ms / args.steps, "merge_ms": merge_ms,
         "counters": {k: cnt[k] for k in ("rejected", "hit_max", "too_early", "accepted",
                                          "escape_iters", "executed_iters", "orbit_points",
@@ -366,21 +392,23 @@ def native_arm(args, wl, rank, world, local_rank):
     # second roofline: red.global.add.u32 rate vs a probe scattering over the same footprint
     red_peak = r.probe_red_peak(cells * 4)
     line["roofline_red"] = {
-        "bound": "l2-red", "unit": "Gred/s", "achieved": cnt["increments"] * scale / t_s / 1e9,
-        "peak": red_peak / 1e9, "frac": cnt["increments"] * scale / t_s / red_peak,
+        "bound": "l2-red", "unit": "Gred/s", "achieved": increments_total * scale / t_s / 1e9,
+        "peak": red_peak / 1e9, "frac": increments_total * scale / t_s / red_peak,
         "footprint_bytes": cells * 4,
         "peak_source": "in-run probe: red.global.add.u32 to uniformly random cells of an array of "
                        "the histogram's size (buddha_probe_red_peak)",
         "algorithmic_bytes_per_increment": 4}
     if world == 1 and not args.skip_baselines:
         r.close()
-        line["cpu_baseline"] = time_cpu_oracle(wl)
-        ref = run_reference_binary(wl, 5.0)
-        if ref:
-            line["reference_cuda"] = {"value": ref[0], "unit": "samples/s", "passes": ref[1],
-                                      "seconds": ref[2],
+        line["cpu_baseline"] = time_cpu_oracle(wl, channels=channels)
+        refs = [run_reference_binary((w, h, mk, ck, canvas, 0), 5.0)
+                for (mk, ck) in (channels or [(m, c)])]
+        if all(refs):
+            line["reference_cuda"] = {"value": 1.0 / sum(1.0 / x[0] for x in refs),
+                                      "unit": "samples/s", "passes": [x[1] for x in refs],
+                                      "seconds": [x[2] for x in refs],
                                       "what": "unmodified cudabrot.cu built for sm_100a, same "
-                                              "workload, this GPU, -t 5"}
+                                              "workload, this GPU, -t 5 (one run per channel)"}
     else:
         r.close()
     print(json.dumps(line), flush=True)

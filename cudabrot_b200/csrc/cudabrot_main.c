@@ -12,6 +12,9 @@
  *   --gpus G          use devices d..d+G-1, disjoint sample ranges, one ncclReduce at the end
  *   --no-shortcut     disable the exact periodicity shortcut (identical output, slower)
  *   --burning-ship    the reference's compile-time RENDER_BURNING_SHIP variant (cudabrot.cu:15-17)
+ *   --channels M1:C1,M2:C2[,...]  fused multi-channel render: one pass over the candidates, one
+ *                     histogram / -s file / PGM per (-m, -c) pair (what the three runs of
+ *                     generate_hires_color_image.sh:27-59 produce); files get a .chK suffix
  * With -s FILE the next sample index is kept in FILE.cursor so a resumed run continues the stream
  * instead of replaying it (the reference re-seeds with 1337 and replays).
  */
@@ -79,6 +82,20 @@ static uint64_t ImageBufferSize(void) {
   return ((uint64_t) g.params.width) * ((uint64_t) g.params.height) * sizeof(uint32_t);
 }
 
+static int Channels(void) { return g.params.n_channels > 1 ? (int) g.params.n_channels : 1; }
+
+/* File of channel k: `base` itself for a plain render, else base with ".ch<k>" appended (-s) or
+ * inserted before the extension (-o: out.pgm -> out.ch0.pgm). */
+static void ChannelFileName(char *dst, size_t n, const char *base, int k, int before_extension) {
+  if (Channels() == 1) {
+    snprintf(dst, n, "%s", base);
+    return;
+  }
+  const char *dot = before_extension ? strrchr(base, '.') : NULL;
+  if (dot && !strchr(dot, '/')) snprintf(dst, n, "%.*s.ch%d%s", (int) (dot - base), base, k, dot);
+  else snprintf(dst, n, "%s.ch%d", base, k);
+}
+
 static void PrintUsage(char *program_name) {
   printf("Usage: %s [options]\n\n", program_name);
   printf("Options may be one or more of the following:\n"
@@ -127,6 +144,8 @@ static void PrintUsage(char *program_name) {
     "  --gpus <G>: Use G GPUs starting at -d; histograms are summed at the end.\n"
     "  --no-shortcut: Disable the exact periodicity shortcut (same output).\n"
     "  --burning-ship: Render the burning ship fractal (RENDER_BURNING_SHIP in the reference).\n"
+    "  --channels <m1:c1,m2:c2,...>: Render up to 4 (-m, -c) pairs in one pass; the -s and -o\n"
+    "      files get a .ch<k> suffix.\n"
     "");
   exit(0);
 }
@@ -261,6 +280,33 @@ static void ParseArguments(int argc, char **argv) {
     }
     if (strcmp(a, "--no-shortcut") == 0) { g.params.flags |= BUDDHA_F_NO_SHORTCUT; continue; }
     if (strcmp(a, "--burning-ship") == 0) { g.params.flags |= BUDDHA_F_BURNING_SHIP; continue; }
+    if (strcmp(a, "--channels") == 0) {
+      if ((i + 1) >= argc) {
+        printf("Argument %s needs a value.\n", a);
+        PrintUsage(argv[0]);
+      }
+      const char *v = argv[++i];
+      uint32_t n = 0;
+      while (*v && n < BUDDHA_MAX_CHANNELS) {
+        char *end = NULL;
+        long m = strtol(v, &end, 10);
+        if (end == v || *end != ':') break;
+        v = end + 1;
+        long c = strtol(v, &end, 10);
+        if (end == v || (*end != ',' && *end != 0)) break;
+        g.params.channel_max[n] = (int32_t) m;
+        g.params.channel_min[n] = (int32_t) c;
+        n++;
+        v = (*end == ',') ? end + 1 : end;
+      }
+      if (*v || n < 2) {
+        printf("--channels needs 2 to %d max:min pairs, e.g. 100:20,1000:20,20000:20\n",
+          BUDDHA_MAX_CHANNELS);
+        PrintUsage(argv[0]);
+      }
+      g.params.n_channels = n;
+      continue;
+    }
     printf("Invalid argument: %s\n", a);
     PrintUsage(argv[0]);
   }
@@ -278,42 +324,46 @@ static void SidecarName(char *dst, size_t n) { snprintf(dst, n, "%s.cursor", g.i
 static void LoadInProgressBuffer(void) {
   if (!g.inprogress_file) return;
   uint64_t expected_size = ImageBufferSize();
-  FILE *f = fopen(g.inprogress_file, "rb");
-  printf("Loading previous image state from %s.\n", g.inprogress_file);
-  if (!f) {
-    if (errno == ENOENT) {
-      printf("File %s doesn't exist yet. Not loading.\n", g.inprogress_file);
-      return;
+  for (int k = 0; k < Channels(); k++) {
+    char file[4096];
+    ChannelFileName(file, sizeof(file), g.inprogress_file, k, 0);
+    FILE *f = fopen(file, "rb");
+    printf("Loading previous image state from %s.\n", file);
+    if (!f) {
+      if (errno == ENOENT) {
+        printf("File %s doesn't exist yet. Not loading.\n", file);
+        return;
+      }
+      printf("Failed opening %s: %s\n", file, strerror(errno));
+      Cleanup();
+      exit(1);
     }
-    printf("Failed opening %s: %s\n", g.inprogress_file, strerror(errno));
-    Cleanup();
-    exit(1);
-  }
-  int64_t file_size = -1;
-  if (fseek(f, 0, SEEK_END) == 0) file_size = ftell(f);
-  if (file_size < 0 || fseek(f, 0, SEEK_SET) != 0) {
-    printf("Failed reading file size: %s\n", strerror(errno));
+    int64_t file_size = -1;
+    if (fseek(f, 0, SEEK_END) == 0) file_size = ftell(f);
+    if (file_size < 0 || fseek(f, 0, SEEK_SET) != 0) {
+      printf("Failed reading file size: %s\n", strerror(errno));
+      fclose(f);
+      Cleanup();
+      exit(1);
+    }
+    if ((uint64_t) file_size != expected_size) {
+      printf("The size of %s doesn't match the expected size of %lu bytes.\n",
+        file, (unsigned long) expected_size);
+      fclose(f);
+      Cleanup();
+      exit(1);
+    }
+    if (fread((char *) g.host_buddhabrot + (uint64_t) k * expected_size, expected_size, 1, f) != 1) {
+      printf("Failed reading %s: %s\n", file, strerror(errno));
+      fclose(f);
+      Cleanup();
+      exit(1);
+    }
     fclose(f);
-    Cleanup();
-    exit(1);
   }
-  if ((uint64_t) file_size != expected_size) {
-    printf("The size of %s doesn't match the expected size of %lu bytes.\n",
-      g.inprogress_file, (unsigned long) expected_size);
-    fclose(f);
-    Cleanup();
-    exit(1);
-  }
-  if (fread(g.host_buddhabrot, expected_size, 1, f) != 1) {
-    printf("Failed reading %s: %s\n", g.inprogress_file, strerror(errno));
-    fclose(f);
-    Cleanup();
-    exit(1);
-  }
-  fclose(f);
   /* the loaded counts go to GPU 0 only; the other GPUs start from zero and are summed in */
   Check(buddha_load_histogram(g.ctx[0], g.host_buddhabrot,
-    (size_t) g.params.width * g.params.height), g.ctx[0], "Loading the histogram");
+    (size_t) g.params.width * g.params.height * Channels()), g.ctx[0], "Loading the histogram");
 
   /* continue the Philox stream where the previous run stopped, if it left a cursor */
   if (!g.have_first) {
@@ -333,20 +383,25 @@ static void LoadInProgressBuffer(void) {
 
 static void SaveInProgressBuffer(uint64_t next_sample) {
   if (!g.inprogress_file) return;
-  printf("Saving in-progress buffer to %s.\n", g.inprogress_file);
-  FILE *f = fopen(g.inprogress_file, "wb");
-  if (!f) {
-    printf("Failed opening %s: %s\n", g.inprogress_file, strerror(errno));
-    Cleanup();
-    exit(1);
-  }
-  if (fwrite(g.host_buddhabrot, ImageBufferSize(), 1, f) != 1) {
-    printf("Failed writing data to %s: %s\n", g.inprogress_file, strerror(errno));
+  for (int k = 0; k < Channels(); k++) {
+    char file[4096];
+    ChannelFileName(file, sizeof(file), g.inprogress_file, k, 0);
+    printf("Saving in-progress buffer to %s.\n", file);
+    FILE *f = fopen(file, "wb");
+    if (!f) {
+      printf("Failed opening %s: %s\n", file, strerror(errno));
+      Cleanup();
+      exit(1);
+    }
+    if (fwrite((char *) g.host_buddhabrot + (uint64_t) k * ImageBufferSize(), ImageBufferSize(), 1,
+               f) != 1) {
+      printf("Failed writing data to %s: %s\n", file, strerror(errno));
+      fclose(f);
+      Cleanup();
+      exit(1);
+    }
     fclose(f);
-    Cleanup();
-    exit(1);
   }
-  fclose(f);
   char name[4096];
   SidecarName(name, sizeof(name));
   FILE *c = fopen(name, "w");
@@ -358,9 +413,9 @@ static void SaveInProgressBuffer(uint64_t next_sample) {
 }
 
 /* SaveImage (cudabrot.cu:548-577).  The pixels arrive big-endian from the tone-map kernel. */
-static void SaveImage(void) {
+static void SaveImage(const char *name) {
   size_t pixel_count = (size_t) g.params.width * g.params.height;
-  FILE *output = fopen(g.output_image, "wb");
+  FILE *output = fopen(name, "wb");
   if (!output) {
     printf("Failed opening output image.\n");
     return;
@@ -376,6 +431,15 @@ static void SaveImage(void) {
     return;
   }
   fclose(output);
+}
+
+/* SetGrayscalePixels (cudabrot.cu:454-468) for one channel, into g.grayscale_image. */
+static void ToneMapChannel(int k) {
+  uint32_t max = 0;
+  double scale = 0;
+  Check(buddha_tonemap_channel_u16(g.ctx[0], k, g.gamma_correction, 1, g.grayscale_image,
+    (size_t) g.params.width * g.params.height, &max, &scale), g.ctx[0], "Tone-mapping");
+  printf("Max value: %lu, scale: %f\n", (unsigned long) max, scale);
 }
 
 /* ---- rendering --------------------------------------------------------------------------- */
@@ -442,18 +506,14 @@ static uint64_t RenderImage(void) {
   }
   if (g.gpus > 1) Check(buddha_merge(g.ctx, g.gpus, 0), g.ctx[0], "Merging the histograms");
   Check(buddha_read_histogram(g.ctx[0], g.host_buddhabrot,
-    (size_t) g.params.width * g.params.height), g.ctx[0], "Reading the histogram");
+    (size_t) g.params.width * g.params.height * Channels()), g.ctx[0], "Reading the histogram");
   double seconds = CurrentSeconds() - start_seconds;
   /* one reference pass = 512*512*50 candidates; keeps "passes * 13107200 / seconds" meaningful */
   printf("%d Buddhabrot passes took %f seconds.\n",
     (int) ((total + REFERENCE_PASS_SAMPLES - 1) / REFERENCE_PASS_SAMPLES), seconds);
   printf("%llu candidate samples on %d GPU(s), %.4e samples/s.\n", (unsigned long long) total,
     g.gpus, (double) total / seconds);
-  uint32_t max = 0;
-  double scale = 0;
-  Check(buddha_tonemap_u16(g.ctx[0], g.gamma_correction, 1, g.grayscale_image,
-    (size_t) g.params.width * g.params.height, &max, &scale), g.ctx[0], "Tone-mapping");
-  printf("Max value: %lu, scale: %f\n", (unsigned long) max, scale);
+  if (Channels() == 1) ToneMapChannel(0);
   /* next unused index: all GPUs' ranges restart from it (plus i * 2^56) on a resumed run */
   uint64_t advance = g.have_samples ? g.samples : 0;
   if (!g.have_samples) {
@@ -474,6 +534,11 @@ int main(int argc, char **argv) {
     printf("Failed setting signal handler.\n");
     return 1;
   }
+  if (Channels() > 1) {  /* the line below names the widest channel, as the fused pass runs */
+    for (int k = 0; k < Channels(); k++)
+      if (k == 0 || g.params.channel_max[k] > g.params.max_iterations)
+        g.params.max_iterations = g.params.channel_max[k];
+  }
   printf("Creating %dx%d image, %d max iterations.\n", g.params.width, g.params.height,
     g.params.max_iterations);
   printf("Calculating image...\n");
@@ -492,7 +557,7 @@ int main(int argc, char **argv) {
       return 1;
     }
   }
-  g.host_buddhabrot = (uint32_t *) calloc(1, ImageBufferSize());
+  g.host_buddhabrot = (uint32_t *) calloc(Channels(), ImageBufferSize());
   g.grayscale_image = (uint16_t *) calloc(pixel_count, sizeof(uint16_t));
   if (!g.host_buddhabrot || !g.grayscale_image) {
     printf("Failed allocating host buffers.\n");
@@ -503,7 +568,16 @@ int main(int argc, char **argv) {
   uint64_t next_sample = RenderImage();
   SaveInProgressBuffer(next_sample);
   printf("Saving image.\n");
-  SaveImage();
+  if (Channels() == 1) {
+    SaveImage(g.output_image);
+  } else {
+    for (int k = 0; k < Channels(); k++) {
+      char name[4096];
+      ChannelFileName(name, sizeof(name), g.output_image, k, 1);
+      ToneMapChannel(k);
+      SaveImage(name);
+    }
+  }
   printf("Done! Output image saved: %s\n", g.output_image);
   Cleanup();
   return 0;

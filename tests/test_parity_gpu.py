@@ -148,6 +148,33 @@ def test_fused_channels_match_separate_oracle_runs(buddha, oracle, case):
             assert (mx, scale) == (omx, oscale) and np.array_equal(img, oimg)
 
 
+def test_cli_fused_channels(buddha, oracle, tmp_path):
+    """--channels: one pass, one -s file and one PGM per channel, each byte-identical to what a
+    single-channel run writes (generate_hires_color_image.sh:27-59 needs three runs)."""
+    cli = buddha.capi.CLI_PATH
+    save, out = str(tmp_path / "state.raw"), str(tmp_path / "img.pgm")
+    channels = [(100, 20), (1000, 20), (5000, 200)]
+    args = [cli, "-w", "240", "-h", "160", "-g", "2.2", "-s", save, "-o", out, "--samples",
+            "400000", "--channels", ",".join("%d:%d" % mc for mc in channels)]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for k, (m, c) in enumerate(channels):
+        ohist, _, _ = oracle.render(240, 160, m, c, 1337, 0, 400000)
+        got = np.fromfile("%s.ch%d" % (save, k), dtype="<u4").reshape(160, 240)
+        assert np.array_equal(got, ohist)
+        oimg, _, _ = oracle.tonemap(ohist, 2.2)
+        opgm = str(tmp_path / "oracle.pgm")
+        oracle.write_pgm(opgm, oimg)
+        assert open(str(tmp_path / ("img.ch%d.pgm" % k)), "rb").read() == open(opgm, "rb").read()
+    # resume: the second run continues the stream and accumulates on top of the loaded channels
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Continuing the sample stream at index 400000." in r.stdout
+    for k, (m, c) in enumerate(channels):
+        ohist, _, _ = oracle.render(240, 160, m, c, 1337, 0, 800000)
+        got = np.fromfile("%s.ch%d" % (save, k), dtype="<u4").reshape(160, 240)
+        assert np.array_equal(got, ohist)
+
+
 def test_fused_rejects_bad_channels(buddha):
     with pytest.raises(buddha.capi.BuddhaError):
         buddha.Renderer(64, 64, channels=[(100, 20), (14, 0)])       # max must exceed the tiers
