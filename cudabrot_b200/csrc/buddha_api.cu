@@ -65,6 +65,7 @@ struct buddha_ctx {
   size_t pool_entries;
   double tile_pts_per_sample;
   uint16_t *d_gray;               // tone-mapped image, allocated on first use
+  uint32_t *d_chan;               // fused contexts: one de-interleaved channel, allocated on first use
   uint16_t *d_lut;
   uint32_t *d_thr;
   uint32_t lut_capacity;
@@ -128,7 +129,6 @@ void fill_render_params(buddha_ctx *c) {
   r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
   r.ship = (p.flags & BUDDHA_F_BURNING_SHIP) ? 1 : 0;
   r.n_ch = c->n_ch > 1 ? c->n_ch : 0;
-  r.ch_stride = (uint32_t)c->ch_cells;
   r.ch_low = p.max_iterations;
   for (int k = 0; k < c->n_ch && c->n_ch > 1; k++) {
     r.ch_max[k] = p.channel_max[k]; r.ch_min[k] = p.channel_min[k];
@@ -370,7 +370,9 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       c->tile_shift = forced ? 12 : 24;  // 16 KB test tiles / 64 MB production tiles
       if ((e = getenv("BUDDHA_TILE_SHIFT"))) c->tile_shift = atoi(e);
       if (c->tile_shift < 8 || c->tile_shift > 28) c->tile_shift = 24;
-      c->n_tiles = (int)((c->cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
+      // fused contexts count tiles in points of n_ch interleaved cells: keep the bytes per tile
+      if (n_ch > 1 && !forced) c->tile_shift -= (n_ch > 2) ? 2 : 1;
+      c->n_tiles = (int)((c->ch_cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
       c->tile_smem = (size_t)c->n_tiles * kWarpsPerCta * sizeof(uint2);
       if (c->n_tiles > 512) {  // not a case tiling is meant for
         buddha_destroy(c);
@@ -429,7 +431,7 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
   if (c->ev_applied[1]) cudaEventDestroy(c->ev_applied[1]);
   cudaFree(c->d_pool); cudaFree(c->d_tcount); cudaFree(c->d_tcap); cudaFree(c->d_tbase);
-  cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr);
+  cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr); cudaFree(c->d_chan);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_ta) cudaEventDestroy(c->ev_ta);
@@ -446,24 +448,32 @@ int buddha_clear_histogram(buddha_ctx *c) {
   return BUDDHA_OK;
 }
 
+// Fused contexts keep the histogram interleaved on the device (uint32[h][w][n_ch]); the host API
+// is channel-major, so every transfer goes through one de-interleaved channel buffer.
+static int channel_buffer(buddha_ctx *c) {
+  if (!c->d_chan) CU(c, cudaMalloc(&c->d_chan, sizeof(uint32_t) * c->ch_cells));
+  return BUDDHA_OK;
+}
+
 int buddha_load_histogram(buddha_ctx *c, const uint32_t *host, size_t cells) {
   if (!c || !host) return BUDDHA_EINVAL;
   if (cells != c->cells)
     return fail(c, BUDDHA_ESIZE, "histogram has %zu cells, canvas needs %zu", cells, c->cells);
   CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemcpyAsync(c->d_hist, host, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                        c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  return BUDDHA_OK;
-}
-
-int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
-  if (!c || !host) return BUDDHA_EINVAL;
-  if (cells != c->cells)
-    return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, canvas has %zu", cells, c->cells);
-  CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemcpyAsync(host, c->d_hist, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                        c->stream));
+  if (c->n_ch > 1) {
+    int rc = channel_buffer(c);
+    if (rc) return rc;
+    for (int k = 0; k < c->n_ch; k++) {
+      CU(c, cudaMemcpyAsync(c->d_chan, host + (size_t)k * c->ch_cells,
+                            c->ch_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      channel_scatter_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
+                                                                     c->ch_cells, c->n_ch, k);
+      CU(c, cudaGetLastError());
+    }
+  } else {
+    CU(c, cudaMemcpyAsync(c->d_hist, host, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                          c->stream));
+  }
   CU(c, cudaStreamSynchronize(c->stream));
   return BUDDHA_OK;
 }
@@ -474,9 +484,28 @@ int buddha_read_channel(buddha_ctx *c, int channel, uint32_t *host, size_t cells
   if (cells != c->ch_cells)
     return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, a channel has %zu", cells, c->ch_cells);
   CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemcpyAsync(host, c->d_hist + (size_t)channel * c->ch_cells, cells * sizeof(uint32_t),
-                        cudaMemcpyDeviceToHost, c->stream));
+  const uint32_t *src = c->d_hist;
+  if (c->n_ch > 1) {
+    int rc = channel_buffer(c);
+    if (rc) return rc;
+    channel_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
+                                                                  c->ch_cells, c->n_ch, channel);
+    CU(c, cudaGetLastError());
+    src = c->d_chan;
+  }
+  CU(c, cudaMemcpyAsync(host, src, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
+}
+
+int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, canvas has %zu", cells, c->cells);
+  for (int k = 0; k < c->n_ch; k++) {
+    int rc = buddha_read_channel(c, k, host + (size_t)k * c->ch_cells, c->ch_cells);
+    if (rc) return rc;
+  }
   return BUDDHA_OK;
 }
 
@@ -539,7 +568,8 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       const int agrid = (int)((c->tile_warps + kApplyWarps - 1) / kApplyWarps);
       for (int t = 0; t < c->n_tiles; t++)
         apply_tile_kernel<<<agrid, kApplyWarps * 32, 0, side>>>(
-            c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift);
+            c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift,
+            rp.n_ch);
       CU(c, cudaEventRecord(c->ev_applied[b], side));
       c->apply_pending[b] = true;
       c->tile_buf = b ^ 1;
@@ -709,11 +739,15 @@ int buddha_get_channel_counters(buddha_ctx *c, int channel, buddha_counters *out
   memset(out, 0, sizeof(*out));
   out->candidates = c->candidates;
   out->rejected = v[kCntRejected];
-  out->hit_max = ch[kChHit];
+  // the device counts, per channel, the samples that ESCAPED beyond the channel's limit; samples
+  // that never escaped (v[kCntHitMax]) hit every channel's limit
+  const unsigned long long widest = (unsigned long long)c->params.max_iterations;
+  const unsigned long long limit = (unsigned long long)c->params.channel_max[channel];
+  out->hit_max = ch[kChHit] + v[kCntHitMax];
   out->accepted = ch[kChAccepted];
-  out->too_early = c->candidates - v[kCntRejected] - ch[kChHit] - ch[kChAccepted];
+  out->too_early = c->candidates - v[kCntRejected] - out->hit_max - ch[kChAccepted];
   // sum over samples of min(steps run, this channel's limit)
-  out->escape_iters = v[kCntEscapeIters] - ch[kChOver];
+  out->escape_iters = v[kCntEscapeIters] - ch[kChOver] - v[kCntHitMax] * (widest - limit);
   out->orbit_points = ch[kChPoints];
   out->increments = ch[kChIncrements];
   out->executed_iters = v[kCntExecuted];
@@ -767,7 +801,15 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
   if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
   if (host_out && cells != c->ch_cells)
     return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->ch_cells);
-  const uint32_t *d_src = c->d_hist + (size_t)channel * c->ch_cells;
+  const uint32_t *d_src = c->d_hist;
+  if (c->n_ch > 1) {
+    int rc = channel_buffer(c);
+    if (rc) return rc;
+    channel_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
+                                                                  c->ch_cells, c->n_ch, channel);
+    CU(c, cudaGetLastError());
+    d_src = c->d_chan;
+  }
   CU(c, cudaSetDevice(c->params.device));
   const int blocks = c->sm_count * 8;
 

@@ -62,12 +62,13 @@ struct RenderParams {
   int32_t shortcut;
   int32_t ship;                 // burning-ship variant (only the simple kernel reads this at run time)
   // fused multi-channel render: channel k accepts a sample that escapes at step `it` iff
-  // ch_min[k] <= it - 1 < ch_max[k]; its histogram starts at hist + k * ch_stride.  max_it /
-  // min_it above are then the largest ch_max / the smallest ch_min.
+  // ch_min[k] <= it - 1 < ch_max[k].  The device histogram is then INTERLEAVED, uint32[h][w][n_ch]:
+  // the (up to n_ch) increments of one orbit point fall into one 32-byte sector instead of n_ch
+  // sectors hundreds of MB apart (the host API transposes: its layout stays channel-major).
+  // max_it / min_it above are the largest ch_max / the smallest ch_min.
   int32_t n_ch;
   int32_t ch_max[kMaxChannels], ch_min[kMaxChannels];
   int32_t ch_low;               // smallest ch_max: below it no channel has hit its limit yet
-  uint32_t ch_stride;           // cells per channel
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
   // tile-binned scatter for histograms much larger than L2 (0 = off, see scatter())
@@ -183,6 +184,25 @@ __device__ __forceinline__ void scatter(const RenderParams &p, const Sink &k, ui
     }
   }
   red_add_u32(k.hist + idx);
+}
+
+// Fused render: one orbit point, `mask` = the channels that take it.  Tiles are counted in POINTS
+// (a tile holds 2^tile_shift points = n_ch << tile_shift cells) and a list entry carries the mask
+// above the tile-local point offset, so a point costs one append however many channels take it.
+__device__ __forceinline__ void scatter_fused(const RenderParams &p, const Sink &k, uint32_t idx,
+                                              unsigned mask) {
+  if (p.tile_shift) {
+    uint2 *e = k.tile_tab + (idx >> p.tile_shift);
+    const uint32_t slot = atomicAdd(&e->x, 1u);
+    if (slot < e->y) {
+      __stcs(p.pool + slot, (idx & ((1u << p.tile_shift) - 1u)) | (mask << kOrbStepBits));
+      return;
+    }
+  }
+  uint32_t *cell = k.hist + (size_t)idx * (uint32_t)p.n_ch;
+#pragma unroll
+  for (int c = 0; c < kMaxChannels; c++)
+    if ((mask >> c) & 1u) red_add_u32(cell + c);
 }
 
 // Per-warp list table: set it up (mode 0: empty lists, mode 1: continue where an earlier kernel
@@ -487,7 +507,10 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
   if constexpr ((kVar & kVarFused) != 0) {
     for (int k = 0; k < p.n_ch; k++) {
       const bool a = (mask >> k) & 1u;
-      channel_add(counters, k, kChAccepted, a ? 1u : 0u);
+      const unsigned n = __popc(__ballot_sync(kFull, a));
+      if (n == 0u) continue;
+      if (lane_id() == 0)
+        atomicAdd(counters + kCntSlots + k * kChSlots + kChAccepted, (unsigned long long)n);
       channel_add(counters, k, kChPoints, a ? (uint32_t)it : 0u);
     }
     n |= (int)(mask << kOrbStepBits);
@@ -495,21 +518,22 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
   push_z(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
 }
 
-// Fused render: a sample has finished its escape test -- it escaped at step it_f, or (hit) it never
-// escaped within max_it.  Channels whose limit lies below that count it as "hit max" and must not
-// be charged the iterations beyond their limit (escape_iters_k = sum of min(it_f, ch_max[k])).
+// Fused render: a sample ESCAPED at step it_f.  Channels whose limit lies below it_f count it as
+// "hit max" and must not be charged the iterations beyond their limit (escape_iters_k = sum of
+// min(it_f, ch_max[k])).  Samples that never escape hit every channel's limit; the host adds
+// those from the common hit counter (buddha_get_channel_counters), so deep stays untouched.
 template <int kVar>
 __device__ __forceinline__ void channel_finish(const RenderParams &p, unsigned long long *counters,
-                                               bool esc, bool hit, int it_f) {
+                                               bool esc, int it_f) {
   if constexpr ((kVar & kVarFused) != 0) {
-    const bool any = hit || (esc && it_f > p.ch_low);
+    const bool any = esc && it_f > p.ch_low;
     if (__ballot_sync(kFull, any) == 0u) return;
-    const int reached = hit ? p.max_it : it_f;
     for (int k = 0; k < p.n_ch; k++) {
-      const bool over = any && reached > p.ch_max[k];
-      const bool h = over || (hit && reached >= p.ch_max[k]);  // the largest channel on a true hit
-      channel_add(counters, k, kChHit, h ? 1u : 0u);
-      channel_add(counters, k, kChOver, over ? (uint32_t)(reached - p.ch_max[k]) : 0u);
+      const bool over = any && it_f > p.ch_max[k];
+      const unsigned n = __popc(__ballot_sync(kFull, over));
+      if (n == 0u) continue;
+      if (lane_id() == 0) atomicAdd(counters + kCntSlots + k * kChSlots + kChHit, (unsigned long long)n);
+      channel_add(counters, k, kChOver, over ? (uint32_t)(it_f - p.ch_max[k]) : 0u);
     }
   }
 }
@@ -667,7 +691,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   const bool hit = surv && nit >= p.max_it;  // ran all max iterations (allowed == max - it)
   ws.n_hit += hit ? 1u : 0u;
   push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, it + cnt);
-  channel_finish<kVar>(p, counters, esc, hit, it + cnt);
+  channel_finish<kVar>(p, counters, esc, it + cnt);
   const bool cont = surv && !hit;
   if (__ballot_sync(kFull, cont)) {
     // deep's no-re-entry argument needs |c| <= 1.99937, and a full unchecked round must fit
@@ -756,7 +780,6 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       ws.skipped += hit ? (uint32_t)(max_it - it) : 0u;
       ws.n_hit += hit ? 1u : 0u;
       ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
-      channel_finish<kVar>(p, counters, false, hit, max_it);
       if (__ballot_sync(kFull, back)) push_z(q.late, ws.late_n, back, cx, cy, x, y, it);
       if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
     }
@@ -775,6 +798,7 @@ struct OrbitLane {
   bool act;
   double cx, cy, x, y;
   int n;
+  uint32_t inc;  // fused render: in-canvas points of this orbit not yet credited to its channels
 };
 
 // One recorded step.  The common path is branch-free (the increment is a predicated reduction), so
@@ -783,7 +807,7 @@ struct OrbitLane {
 // (fused render: o.n carries the channel mask above bit kOrbStepBits; the point goes to every
 // accepting channel's histogram)
 template <int kVar>
-__device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane &o, WarpState &ws,
+__device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                           const Sink &hist) {
   // division-free binning, see bin_point
   const double tch = __fma_rn(o.x, p.inv_half_re, p.c0_hi_re);
@@ -808,14 +832,8 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane
       ws.n_exact += 1u;
       in = bin_exact_index(o.x, o.y, p, &idx);
     }
-    const unsigned mask = (unsigned)o.n >> kOrbStepBits;
-    ws.p_inc += in ? 1u : 0u;
-#pragma unroll
-    for (int k = 0; k < kMaxChannels; k++) {
-      const bool a = in && ((mask >> k) & 1u);
-      if (a) scatter(p, hist, idx + (uint32_t)k * p.ch_stride);
-      ws.ch_inc[k] += a ? 1u : 0u;
-    }
+    o.inc += in ? 1u : 0u;
+    if (in) scatter_fused(p, hist, idx, (unsigned)o.n >> kOrbStepBits);
   } else {
     if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
     ws.p_inc += hit ? 1u : 0u;
@@ -823,6 +841,19 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, const OrbitLane
       ws.n_exact += 1u;
       ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
     }
+  }
+}
+
+// Fused render: credit the in-canvas points an orbit has collected to the channels in its mask
+// (per orbit, not per point).  Call before o.n is overwritten or given away.
+template <int kVar>
+__device__ __forceinline__ void orbit_credit(OrbitLane &o, WarpState &ws) {
+  if constexpr ((kVar & kVarFused) != 0) {
+    const unsigned mask = (unsigned)o.n >> kOrbStepBits;
+    ws.p_inc += o.inc;
+#pragma unroll
+    for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] += ((mask >> k) & 1u) ? o.inc : 0u;
+    o.inc = 0;
   }
 }
 
@@ -838,7 +869,7 @@ __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, 
 template <int kVar>
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                             const Sink &hist) {
-  OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0};
+  OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0, 0u};
 #pragma unroll 1
   for (;;) {
     if (ws.orb_n > 0 && __ballot_sync(kFull, !o.act)) {
@@ -846,6 +877,7 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
       int rank = __popc(m & lanemask_lt());
       if (!o.act && rank < ws.orb_n) {
         const int slot = ws.orb_n - 1 - rank;
+        orbit_credit<kVar>(o, ws);
         double2 c = q.orb.c[slot], z = q.orb.z[slot];
         o.cx = c.x; o.cy = c.y; o.x = z.x; o.y = z.y; o.n = q.orb.it[slot];
         o.act = true;
@@ -858,6 +890,7 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     orbit_step<kVar>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
     orbit_step<kVar>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
+  orbit_credit<kVar>(o, ws);
   if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
 }
@@ -999,13 +1032,14 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
       }
     }
     if (__ballot_sync(kFull, n > 0) == 0u) break;
-    OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, (int)(mask << kOrbStepBits) | 1};
+    OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, (int)(mask << kOrbStepBits) | 1, 0u};
 #pragma unroll 1
     for (int k = 0; k < g; k++) {
       BUDDHA_ZSTEP(x, y, cx, cy);
       if (sub == k) { o.x = x; o.y = y; }
     }
     orbit_bin<kVar>(p, o, ws, sink);
+    orbit_credit<kVar>(o, ws);
     n -= g;
   }
   tile_counters_store(p, sink);
@@ -1023,20 +1057,50 @@ constexpr int kApplyWarps = 4;
 __global__ void __launch_bounds__(kApplyWarps * 32)
 apply_tile_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ tcount,
                   const uint32_t *__restrict__ tile_cap, const uint32_t *__restrict__ tile_base,
-                  const uint32_t *__restrict__ pool, int t, uint32_t n_warps, int tile_shift) {
+                  const uint32_t *__restrict__ pool, int t, uint32_t n_warps, int tile_shift,
+                  int n_ch) {
   const uint32_t w = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
   if (w >= n_warps) return;
   const uint32_t cap = tile_cap[t];
   const uint32_t n = min(tcount[(size_t)t * n_warps + w], cap);
   const uint32_t *src = pool + (tile_base[t] + w * cap);
-  uint32_t *tile = hist + ((size_t)t << tile_shift);
   uint32_t i = lane_id();
+  if (n_ch) {
+    // fused render: entry = tile-local point | channel mask << 28; the point's cells are adjacent
+    uint32_t *tile = hist + ((size_t)t << tile_shift) * (uint32_t)n_ch;
+    for (; i < n; i += 32) {
+      const uint32_t e = __ldcs(src + i);
+      uint32_t *cell = tile + (size_t)(e & ((1u << kOrbStepBits) - 1u)) * (uint32_t)n_ch;
+#pragma unroll
+      for (int c = 0; c < kMaxChannels; c++)
+        if ((e >> (kOrbStepBits + c)) & 1u) red_add_u32(cell + c);
+    }
+    return;
+  }
+  uint32_t *tile = hist + ((size_t)t << tile_shift);
   for (; i + 96 < n; i += 128) {
     uint32_t a = __ldcs(src + i), b = __ldcs(src + i + 32), c = __ldcs(src + i + 64),
              d = __ldcs(src + i + 96);
     red_add_u32(tile + a); red_add_u32(tile + b); red_add_u32(tile + c); red_add_u32(tile + d);
   }
   for (; i < n; i += 32) red_add_u32(tile + __ldcs(src + i));
+}
+
+// Channel <-> interleaved layout of a fused context: out[i] = hist[i * n_ch + ch] and back.
+__global__ void __launch_bounds__(256)
+channel_gather_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ out, size_t cells,
+                      int n_ch, int ch) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
+    out[i] = hist[i * (size_t)n_ch + ch];
+}
+
+__global__ void __launch_bounds__(256)
+channel_scatter_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ in, size_t cells,
+                       int n_ch, int ch) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
+    hist[i * (size_t)n_ch + ch] = in[i];
 }
 
 // ---- tone-map (cudabrot.cu:416-468) ----------------------------------------------------------
