@@ -221,6 +221,62 @@ def test_full_size_cfg3_histogram(buddha, oracle):
     assert int(hist.sum(dtype=np.uint64)) == cnt["increments"]
 
 
+def test_full_size_properties_cfg2(buddha):
+    """BASELINE config 2 at its full canvas and 2^30 samples, where the oracle would need minutes:
+    size-independent properties instead.  One call == any split into calls; the histogram sum ==
+    the increments counted; every candidate ends in exactly one class; the exact shortcut and the
+    division-free binning change nothing (checked on a 2^27-sample prefix)."""
+    w = h = 4000
+    n = 1 << 30
+    with buddha.Renderer(w, h, 20000, 10000) as r:
+        r.render_samples(0, n)
+        whole, cnt = r.read_histogram(), r.counters()
+    assert int(whole.sum(dtype=np.uint64)) == cnt["increments"]
+    assert cnt["candidates"] == n == (cnt["rejected"] + cnt["hit_max"] + cnt["too_early"] +
+                                      cnt["accepted"])
+    assert cnt["orbit_points"] >= cnt["increments"] > 0
+    assert cnt["orbit_points"] >= 10001 * cnt["accepted"]         # every accepted i >= min
+    with buddha.Renderer(w, h, 20000, 10000) as r:
+        cuts = [0, 12345, 4096 * 1000 + 7, 1 << 29, n]
+        for a, b in zip(cuts, cuts[1:]):
+            r.render_samples(a, b - a)
+        parts, cnt2 = r.read_histogram(), r.counters()
+    assert np.array_equal(whole, parts)
+    for k in COUNTER_KEYS:
+        assert cnt[k] == cnt2[k], k
+    m = 1 << 27
+    ref = None
+    for flags in (0, buddha.F_NO_SHORTCUT, buddha.F_EXACT_BINNING):
+        with buddha.Renderer(w, h, 20000, 10000, flags=flags) as r:
+            r.render_samples(1 << 40, m)
+            hist, c = r.read_histogram(), r.counters()
+        if ref is None:
+            ref = (hist, c)
+        else:
+            assert np.array_equal(ref[0], hist)
+            for k in COUNTER_KEYS:
+                assert ref[1][k] == c[k], k
+
+
+def test_full_size_properties_cfg3_tiled_vs_direct(buddha, monkeypatch):
+    """BASELINE config 3 at its full 20000x20000 canvas: the tile-binned scatter (default for
+    1.6 GB) and the direct reductions must produce the same histogram over 2^28 samples, across the
+    calibration launch and a multi-launch pipeline."""
+    n = (1 << 28) + 4097
+    with buddha.Renderer(20000, 20000, 2000, 20) as r:
+        r.render_samples(0, n)
+        tiled, cnt = r.read_histogram(), r.counters()
+    assert int(tiled.sum(dtype=np.uint64)) == cnt["increments"]
+    monkeypatch.setenv("BUDDHA_TILE_MIN_MB", "1000000")
+    with buddha.Renderer(20000, 20000, 2000, 20) as r:
+        r.render_samples(0, 1 << 27)
+        r.render_samples(1 << 27, n - (1 << 27))
+        direct, cnt2 = r.read_histogram(), r.counters()
+    assert np.array_equal(tiled, direct)
+    for k in COUNTER_KEYS:
+        assert cnt[k] == cnt2[k], k
+
+
 def test_load_accumulate_read_roundtrip(buddha, oracle):
     """-s semantics (cudabrot.cu:215-280): a loaded buffer is accumulated into, not replaced."""
     rng = np.random.default_rng(5)
