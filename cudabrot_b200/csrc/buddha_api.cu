@@ -256,6 +256,9 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   const char *why = nullptr;
   double dre = 0, dim = 0;
   if (buddha_validate_canvas(p, &dre, &dim, &why)) return fail(nullptr, BUDDHA_EINVAL, "%s", why);
+  // iteration counts are 32-bit ints as in the reference; the kernels add up to one round on top
+  if (p->max_iterations > 0x7fffffff - 4 * kBlock)
+    return fail(nullptr, BUDDHA_EINVAL, "max iterations must stay below 2^31 - %d", 4 * kBlock);
   // the reference indexes pixels with 32-bit int (cudabrot.cu:312, :551)
   if ((uint64_t)p->width * (uint64_t)p->height > 0x7fffffffull)
     return fail(nullptr, BUDDHA_EINVAL, "width*height exceeds 2^31-1 cells");

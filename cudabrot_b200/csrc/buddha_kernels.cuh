@@ -29,11 +29,12 @@ constexpr int kStackCap = 64;                  // entries per work stack (5 stac
 constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
 constexpr int kGenSteps = 2;                   // escape-test steps done by the sampler itself
 constexpr int kT1End = 6;                      // tier 1 covers steps kGenSteps+1 .. kT1End
-constexpr int kT2End = 14;                     // tier 2 covers steps kT1End+1 .. kT2End
-constexpr int kLateSteps = 16;                 // per-step-tested steps per `late` batch
-constexpr int kBlock = 16;                     // unchecked steps per deep round (= kLateSteps)
-constexpr int kDeepExit = 24;                  // leave a phase when fewer lanes than this are busy
-constexpr int kOrbExit = 16;
+constexpr int kT2End = 22;                     // tier 2 covers steps kT1End+1 .. kT2End
+constexpr int kLateSteps = 24;                 // per-step-tested steps per `late` batch
+constexpr int kBlock = 24;                     // unchecked steps per deep round (= kLateSteps)
+constexpr int kDeepExit = 30;                  // leave a phase when fewer lanes than this are busy
+constexpr int kOrbExit = 24;                   // (tier ends, kBlock and the two exits: measured sweep,
+                                               //  profiles/r01_summary.md)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxChannels = 4;                // fused multi-channel render
 constexpr int kOrbStepBits = 28;               // fused: orbit entries carry (mask << 28) | steps
@@ -356,14 +357,14 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 // six phases.  The escape test of a fresh candidate is a chain of fixed-length, straight-line
 // TIERS: all 32 lanes run the same number of steps with the exact per-step test and no per-lane
 // refill, survivors are ballot-compacted onto the next stack.  The survival curve is so flat
-// (33 % survive step 1, 19 % step 2, 9.8 % step 6, 3.1 % step 14, 1.8 % step 30) that a tier
-// keeps 65..78 % of its lane-steps useful, while the bookkeeping per step drops to one predicated
+// (33 % survive step 1, 19 % step 2, 6.5 % step 6, 2.3 % step 22, 1.5 % step 46) that a tier
+// keeps 55..78 % of its lane-steps useful, while the bookkeeping per step drops to one predicated
 // add and one predicate update.
 //
 //   gen     draw 32 candidates (Philox), cardioid/bulb test, steps 1..2      -> t1 (c only)
 //   tier 1  steps 3..6  (re-computes steps 1..2 from c: 8 FP64, saves 16 B)  -> t2 (c only)
-//   tier 2  steps 7..14 (re-computes steps 1..6)                             -> late
-//   late    16 per-step-tested steps from a stored state (c, z, it): tier-2 survivors, samples
+//   tier 2  steps 7..22 (re-computes steps 1..6)                             -> late
+//   late    24 per-step-tested steps from a stored state (c, z, it): tier-2 survivors, samples
 //           handed back by deep, tails that have fewer than kBlock steps left -> deep / late
 //   deep    long escape tests: kBlock unchecked steps (4 FP64 instr each) per round, one |z|^2
 //           test per round, exact periodicity shortcut, per-lane refill.  A lane whose round
@@ -662,7 +663,7 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
   __syncwarp();
 }
 
-// (b') 16 per-step-tested steps from a stored state.  Entries: tier-2 survivors (it = 14), samples
+// (b') kLateSteps per-step-tested steps from a stored state.  Entries: tier-2 survivors (it = 22), samples
 // handed back by deep (certain to escape within kBlock steps), tails (fewer than kBlock steps left
 // below max), samples that deep cannot take (|c| too close to 2, or deep full right now).
 template <int kVar>
@@ -782,6 +783,9 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
       if (__ballot_sync(kFull, back)) push_z(q.late, ws.late_n, back, cx, cy, x, y, it);
       if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
+      // the per-lane 32-bit counters are flushed at every cursor grab; with a very large -m a few
+      // never-escaping samples could wrap them before that
+      if (__ballot_sync(kFull, ((ws.steps | ws.skipped) >> 30) != 0u)) flush_counters(ws, counters);
     }
   }
   {

@@ -63,7 +63,7 @@ typedef struct {
    * uint32[n_channels][h][w] at this API (on the device it is interleaved, uint32[h][w][n_channels],
    * which is what buddha_device_histogram points to); channel k is bit-identical to what a single-channel context with
    * (-m channel_max[k], -c channel_min[k]) renders from the same sample indices.  Every
-   * channel_max must be > 14 and < 2^28.  0 or 1 = the plain single-channel render. */
+   * channel_max must be > 22 and < 2^28.  0 or 1 = the plain single-channel render. */
   uint32_t n_channels;
   int32_t channel_max[BUDDHA_MAX_CHANNELS];
   int32_t channel_min[BUDDHA_MAX_CHANNELS];

@@ -57,11 +57,13 @@ def test_histogram_and_counters_match_oracle(buddha, oracle, name):
     assert_same(hist, cnt, ohist, ocnt)
 
 
-@pytest.mark.parametrize("m", [2, 3, 5, 6, 7, 13, 14, 15, 17, 29, 30, 31, 45, 46, 47, 62])
+@pytest.mark.parametrize("m", [2, 3, 5, 6, 7, 13, 14, 15, 21, 22, 23, 24, 45, 46, 47, 48, 69,
+                               70, 71, 94])
 def test_tier_boundaries(buddha, oracle, m):
-    """max-iter on, just below and just above every tier boundary of the escape test (2, 6, 14,
-    30, 46, ...), with cutoffs that accept escapes inside the first tiers."""
-    for c in (0, 1, 2, 5, 6, 13, 14):
+    """max-iter on, just below and just above every tier boundary of the escape test (2, 6, 22,
+    then batches / rounds of 24: 46, 70, 94 ...), with cutoffs that accept escapes inside the
+    first tiers."""
+    for c in (0, 1, 2, 5, 6, 21, 22, 45):
         if c >= m:
             continue
         n = (1 << 17) + 77
@@ -116,9 +118,9 @@ def test_burning_ship_matches_oracle(buddha, oracle, extra):
 FUSED_CASES = [
     # (w, h, canvas, channels [(max, min)], samples, flags)
     (500, 400, FULL, [(100, 20), (1000, 20), (20000, 20)], 1 << 21, ""),       # config 5's trio
-    (333, 77, (-1.7, 0.3, -0.123, 0.777), [(3000, 50), (15, 0), (400, 399)], 300007, ""),
+    (333, 77, (-1.7, 0.3, -0.123, 0.777), [(3000, 50), (23, 0), (400, 399)], 300007, ""),
     (256, 256, FULL, [(60, 30), (2000, 1000)], 1 << 20, "F_NO_SHORTCUT"),      # disjoint windows
-    (700, 500, FULL, [(300, 10), (5000, 100), (40, 5), (17, 16)], (1 << 21) + 5, "F_FORCE_TILED"),
+    (700, 500, FULL, [(300, 10), (5000, 100), (40, 5), (25, 24)], (1 << 21) + 5, "F_FORCE_TILED"),
     (300, 300, SHIP_CANVAS, [(200, 10), (5000, 200)], 1 << 19, "F_BURNING_SHIP"),
 ]
 
@@ -177,7 +179,7 @@ def test_cli_fused_channels(buddha, oracle, tmp_path):
 
 def test_fused_rejects_bad_channels(buddha):
     with pytest.raises(buddha.capi.BuddhaError):
-        buddha.Renderer(64, 64, channels=[(100, 20), (14, 0)])       # max must exceed the tiers
+        buddha.Renderer(64, 64, channels=[(100, 20), (22, 0)])       # max must exceed the tiers
     with pytest.raises(buddha.capi.BuddhaError):
         buddha.Renderer(64, 64, channels=[(100, 20)] * 5)
 
