@@ -521,7 +521,13 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     int grid = (int)std::min<uint64_t>(want, (uint64_t)c->sm_count * 32);
     render_simple_kernel<<<grid, 256, 0, c->stream>>>(rp, first, c->d_hist, c->d_counters);
   } else {
-    // the cursor starts at `first`; warps take kChunk indices at a time until it passes rp.end
+    // the cursor starts at `first`; warps take rp.chunk indices at a time until it passes rp.end:
+    // at least ~8 chunks per warp of the full grid, between kMinChunk and kMaxChunk
+    {
+      uint64_t per = count / ((uint64_t)c->grid * kWarpsPerCta * 8);
+      per = std::min<uint64_t>(std::max<uint64_t>(per, kMinChunk), kMaxChunk);
+      rp.chunk = (uint32_t)(per / 32 * 32);
+    }
     unsigned long long start = first;
     CU(c, cudaMemcpyAsync(c->d_cursor, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     const int b = c->tile_buf;  // which half of the list pool / which spill list this launch uses
@@ -536,7 +542,7 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       CU(c, cudaMemsetAsync(rp.tcount, 0, sizeof(uint32_t) * c->n_lists, c->stream));
     }
     CU(c, cudaMemsetAsync(c->spill[b].count, 0, sizeof(unsigned int) * 2, c->stream));
-    uint64_t want = (count + kChunk - 1) / kChunk;  // warps that can get work at all
+    uint64_t want = (count + rp.chunk - 1) / rp.chunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
     const size_t dyn = c->tiled ? c->tile_smem : 0;

@@ -26,13 +26,14 @@ constexpr int kWarpsPerCta = 11;                // 2 CTAs x 11 warps x 10 KB of 
 constexpr int kCtasPerSm = 2;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kStackCap = 64;                  // entries per work stack (5 stacks per warp)
-constexpr int kChunk = 4096;                   // sample indices a warp takes per cursor grab
+constexpr int kChunk = 4096;                   // granularity of launch sizes (host side)
+constexpr int kMinChunk = 1024, kMaxChunk = 16384;  // sample indices a warp takes per cursor grab
 constexpr int kGenSteps = 2;                   // escape-test steps done by the sampler itself
 constexpr int kT1End = 6;                      // tier 1 covers steps kGenSteps+1 .. kT1End
 constexpr int kT2End = 22;                     // tier 2 covers steps kT1End+1 .. kT2End
 constexpr int kLateSteps = 24;                 // per-step-tested steps per `late` batch
 constexpr int kBlock = 24;                     // unchecked steps per deep round (= kLateSteps)
-constexpr int kDeepExit = 30;                  // leave a phase when fewer lanes than this are busy
+constexpr int kDeepExit = 31;                  // leave a phase when fewer lanes than this are busy
 constexpr int kOrbExit = 24;                   // (tier ends, kBlock and the two exits: measured sweep,
                                                //  profiles/r01_summary.md)
 constexpr unsigned kFull = 0xffffffffu;
@@ -72,6 +73,9 @@ struct RenderParams {
   int32_t ch_low;               // smallest ch_max: below it no channel has hit its limit yet
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
+  uint32_t chunk;               // sample indices a warp takes per cursor grab (multiple of 32):
+                                // large for few atomics and counter flushes, small enough that
+                                // every warp of the grid gets several chunks
   // tile-binned scatter for histograms much larger than L2 (0 = off, see scatter())
   int32_t tile_shift;           // log2(cells per tile)
   int32_t n_tiles;
@@ -571,12 +575,12 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
       flush_counters(ws, counters);
       flush_channel_counters<kVar>(p, ws, counters);
       unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)p.chunk);
       base = __shfl_sync(kFull, base, 0);
       if (base >= p.end) { ws.exhausted = true; break; }
       ws.chunk_base = base;
       ws.chunk_off = 0;
-      ws.chunk_len = (base + kChunk <= p.end) ? (uint32_t)kChunk : (uint32_t)(p.end - base);
+      ws.chunk_len = (base + p.chunk <= p.end) ? p.chunk : (uint32_t)(p.end - base);
     }
     const uint32_t o = ws.chunk_off + lane;
     const bool valid = o < ws.chunk_len;
