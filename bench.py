@@ -2,7 +2,7 @@
 """bench.py -- candidate samples/s (and orbit points/s) of the Buddhabrot hot path on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--workload cfg2|cfg1|cfg3|cfg3_m20000|cfg4|cfg5a|cfg5b|cfg5c]
+                    [--workload cfg2|cfg1|cfg3|cfg3_m20000|cfg4|cfg5|cfg5a|cfg5b|cfg5c|cfg5_4k...]
 
 A "step" renders one batch of candidate samples (a fresh block of Philox sample indices per step
 and per rank) into the resident histogram.  N>1: one process per GPU (torchrun), disjoint sample
@@ -45,9 +45,15 @@ WORKLOADS = {
     "cfg5c": (10000, 10000, 20000, 20, FULL, 1 << 32),
     # config 5 as ONE fused pass: every candidate is rendered once into the three channels
     "cfg5": (10000, 10000, 20000, 20, FULL, 1 << 32),
+    # the same trio on a canvas whose three histograms fit L2 together (192 MB), fused and apart
+    "cfg5_4k": (4000, 4000, 20000, 20, FULL, 1 << 32),
+    "cfg5_4k_a": (4000, 4000, 100, 20, FULL, 1 << 32),
+    "cfg5_4k_b": (4000, 4000, 1000, 20, FULL, 1 << 32),
+    "cfg5_4k_c": (4000, 4000, 20000, 20, FULL, 1 << 32),
 }
 # fused multi-channel workloads: [(max-iter, min-cutoff)] per channel (BASELINE.json configs[4])
-CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)]}
+CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)],
+            "cfg5_4k": [(100, 20), (1000, 20), (20000, 20)]}
 REFERENCE_PASS = 13107200  # 512 blocks * 512 threads * 50 samples, cudabrot.cu:20,23,34
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_persistent_kernel launch over 2^30
 # samples, from the `ncu --set full` captures summarised in profiles/r01_summary.md
