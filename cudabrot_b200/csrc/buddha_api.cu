@@ -3,6 +3,14 @@
 // Each export cites the reference call site it replaces in include/buddha.h.  This file owns the
 // device memory, the stream and the launch policy; the kernels are in buddha_kernels.cuh.
 // There is no CPU fallback anywhere in this library.
+//
+// Environment switches (tuning / experiments; none changes a result):
+//   BUDDHA_TILE_MIN_MB        histogram size from which the tile-binned scatter is used (768)
+//   BUDDHA_TILE_SHIFT         log2(cells per tile) (24 = 64 MB)
+//   BUDDHA_TILE_POOL_MB       size of the list pool (min(16 GB, free/4))
+//   BUDDHA_TILE_LAUNCH_LOG2   log2 of the largest launch of the tiled pipeline (30)
+//   BUDDHA_TILE_SERIAL        apply / drain on the render stream (needed under ncu kernel replay)
+//   BUDDHA_PAD_SMEM           extra dynamic shared memory per CTA (occupancy experiments)
 #include "../../include/buddha.h"
 #include "buddha_kernels.cuh"
 
@@ -95,7 +103,7 @@ int fail(buddha_ctx *ctx, int code, const char *fmt, ...) {
                   cudaGetErrorString(e_), __FILE__, __LINE__, #call);                       \
   } while (0)
 
-// Constants of the division-free binning for one axis (see bin_point and DESIGN.md section 4).
+// Constants of the division-free binning for one axis (see orbit_bin and DESIGN.md section 4).
 // T = fma(X, inv_half, c0) = (X/2 - min) * inv + 1.5*2^40 +- 2^-11, rounded onto the 2^-12 grid.
 FastBin make_fast_bin(double min_v, double delta, int n) {
   FastBin f;

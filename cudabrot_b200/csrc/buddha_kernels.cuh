@@ -264,37 +264,6 @@ __device__ __forceinline__ bool bin_exact(double x2, double y2, const RenderPara
   return true;
 }
 
-// Division-free binning.  For each axis two roundings of (quotient +- 2^-11) onto a 2^-12 grid are
-// produced by one DFMA each; if both floors agree, that floor is the reference's truncated IEEE
-// quotient, otherwise the point takes bin_exact.  Returns true if a cell
-// was incremented; *exact is set when the slow path was needed.
-__device__ __forceinline__ bool bin_point(double x2, double y2, const RenderParams &p,
-                                          const Sink &hist, bool *exact) {
-  double tch = __fma_rn(x2, p.inv_half_re, p.c0_hi_re);
-  double tcl = __fma_rn(x2, p.inv_half_re, p.c0_lo_re);
-  double trh = __fma_rn(y2, p.inv_half_im, p.c0_hi_im);
-  double trl = __fma_rn(y2, p.inv_half_im, p.c0_lo_im);
-  // in-range <=> high words equal that of 1.5*2^40 (quotient + eps in [0, 2^20))
-  if (((uint32_t)__double2hiint(tch) != kBinHiWord) | ((uint32_t)__double2hiint(trh) != kBinHiWord))
-    return false;
-  uint32_t ch = (uint32_t)__double2loint(tch), cl = (uint32_t)__double2loint(tcl);
-  uint32_t rh = (uint32_t)__double2loint(trh), rl = (uint32_t)__double2loint(trl);
-  // the low-side values must sit in the same binade (else quotient - eps < 0: boundary hazard)
-  bool same = (((ch ^ cl) | (rh ^ rl)) >> kBinFracBits) == 0u &&
-              (uint32_t)__double2hiint(tcl) == kBinHiWord &&
-              (uint32_t)__double2hiint(trl) == kBinHiWord;
-  if (!same) {
-    *exact = true;
-    return bin_exact(x2, y2, p, hist);
-  }
-  uint32_t col = ch >> kBinFracBits, row = rh >> kBinFracBits;
-  if (col < (uint32_t)p.w && row < (uint32_t)p.h) {
-    scatter(p, hist, row * (uint32_t)p.w + col);
-    return true;
-  }
-  return false;
-}
-
 // ---- the simple kernel (debug / cross-check): one sample per thread, reference dataflow ------
 
 __global__ void __launch_bounds__(256)
@@ -821,7 +790,10 @@ struct OrbitLane {
   uint32_t inc;  // fused render: in-canvas points of this orbit not yet credited to its channels
 };
 
-// One recorded step.  The common path is branch-free (the increment is a predicated reduction), so
+// Division-free binning of one orbit point.  For each axis two roundings of (quotient +- 2^-11)
+// onto a 2^-12 grid are produced by one DFMA each; if both floors agree, that floor is the
+// reference's truncated IEEE quotient, otherwise the point takes
+// bin_exact_index.  The common path is branch-free (the increment is a predicated reduction), so
 // the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
 // the rare exact-binning case branches.
 // (fused render: o.n carries the channel mask above bit kOrbStepBits; the point goes to every
@@ -829,7 +801,6 @@ struct OrbitLane {
 template <int kVar>
 __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                           const Sink &hist) {
-  // division-free binning, see bin_point
   const double tch = __fma_rn(o.x, p.inv_half_re, p.c0_hi_re);
   const double tcl = __fma_rn(o.x, p.inv_half_re, p.c0_lo_re);
   const double trh = __fma_rn(o.y, p.inv_half_im, p.c0_hi_im);
