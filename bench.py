@@ -209,6 +209,9 @@ def reference_arm(args, wl, rank):
                                            "reference has no CPU path)" % (sum(r[1] for r in runs), t)},
                 "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
+        # cudabrot has no CPU implementation; for completeness the CPU restatement of its kernel
+        # logic (OpenMP, all host threads) on a bounded sample of the same workload
+        line["cpu_port"] = time_cpu_oracle(wl, budget_s=8.0)
     else:
         # no GPU build of the reference available: time the CPU port with all host threads
         cb = time_cpu_oracle(wl, budget_s=10.0 * max(1, args.steps))
