@@ -327,8 +327,11 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
                                (const void *)render_persistent_kernel<2>,
                                (const void *)render_persistent_kernel<3>};
   const void *render_fn = render_fns[c->variant];
-  cudaError_t st = cudaFuncSetAttribute(render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)prop.sharedMemPerBlockOptin);
+  cudaFuncAttributes fattr;
+  cudaError_t st = cudaFuncGetAttributes(&fattr, render_fn);
+  if (st == cudaSuccess)
+    st = cudaFuncSetAttribute(render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(prop.sharedMemPerBlockOptin - fattr.sharedSizeBytes));
   if (st == cudaSuccess)
     st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_fn, kThreadsPerCta,
                                                        c->render_smem + c->smem_pad);
