@@ -5,7 +5,7 @@
 // There is no CPU fallback anywhere in this library.
 //
 // Environment switches (tuning / experiments; none changes a result):
-//   BUDDHA_TILE_MIN_MB        histogram size from which the tile-binned scatter is used (768)
+//   BUDDHA_TILE_MIN_MB        histogram size from which the tile-binned scatter is used (640)
 //   BUDDHA_TILE_SHIFT         log2(cells per tile) (24 = 64 MB)
 //   BUDDHA_TILE_POOL_MB       size of the list pool (min(16 GB, free/4))
 //   BUDDHA_TILE_LAUNCH_LOG2   log2 of the largest launch of the tiled pipeline (30)
@@ -373,9 +373,9 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   }
   CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
   {
-    // tile-binned scatter: on for histograms >= 768 MB (config 3: 1.6 GB), or when forced (tests)
+    // tile-binned scatter: on for histograms >= 640 MB (config 3: 1.6 GB; crossover measured with tools/gpu_threshold.py), or when forced (tests)
     const char *e;
-    size_t min_mb = 768;
+    size_t min_mb = 640;
     if ((e = getenv("BUDDHA_TILE_MIN_MB"))) min_mb = (size_t)strtoull(e, nullptr, 10);
     const bool forced = (p->flags & BUDDHA_F_FORCE_TILED) != 0;
     c->tiled = !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
