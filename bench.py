@@ -36,7 +36,7 @@ FULL = (-2.0, 2.0, -2.0, 2.0)
 # name -> (w, h, max_iter, min_iter, canvas, default samples per step per GPU) ; BASELINE.json configs
 WORKLOADS = {
     "cfg1": (1000, 1000, 100, 20, FULL, 1 << 32),
-    "cfg2": (4000, 4000, 20000, 10000, FULL, 1 << 34),
+    "cfg2": (4000, 4000, 20000, 10000, FULL, 1 << 35),
     "cfg3": (20000, 20000, 2000, 20, FULL, 1 << 32),
     "cfg3_m20000": (20000, 20000, 20000, 20, FULL, 1 << 32),
     "cfg4": (8000, 4000, 5000, 20, (0.0, 1.0, 0.0, 0.5), 1 << 32),

