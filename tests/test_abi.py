@@ -31,7 +31,9 @@ def test_library_exports_every_declared_symbol(buddha):
 
 def test_no_torch_or_oracle_dependency(buddha):
     ldd = subprocess.run(["ldd", buddha.capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "torch" not in ldd and "oracle" not in ldd and "c10" not in ldd
+    # library names only: the load addresses ldd prints may contain "c10" by chance
+    names = " ".join(line.split("=>")[0].split("(")[0].strip() for line in ldd.splitlines())
+    assert "torch" not in names and "oracle" not in names and "c10" not in names
     for src in ("buddha_api.cu", "buddha_kernels.cuh", "cudabrot_main.c"):
         text = open(os.path.join(ROOT, "cudabrot_b200", "csrc", src)).read()
         assert "oracle" not in text.lower(), src
