@@ -34,7 +34,7 @@ constexpr int kT2End = 22;                     // tier 2 covers steps kT1End+1 .
 constexpr int kLateSteps = 24;                 // per-step-tested steps per `late` batch
 constexpr int kBlock = 24;                     // unchecked steps per deep round (= kLateSteps)
 constexpr int kDeepExit = 31;                  // leave a phase when fewer lanes than this are busy
-constexpr int kOrbExit = 24;                   // (tier ends, kBlock and the two exits: measured sweep,
+constexpr int kOrbExit = 28;                   // (tier ends, kBlock and the two exits: measured sweep,
                                                //  profiles/r01_summary.md)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxChannels = 4;                // fused multi-channel render
