@@ -545,8 +545,8 @@ int main(int argc, char **argv) {
   size_t pixel_count = (size_t) g.params.width * g.params.height;
   /* no per-thread RNG state: the GPU holds the histogram and, later, the 16-bit image */
   printf("Approximate memory needed: %.03f MiB GPU, %.03f MiB CPU\n",
-    (float) (ImageBufferSize() + pixel_count * sizeof(uint16_t)) / (1024.0 * 1024.0),
-    (float) (ImageBufferSize() + pixel_count * sizeof(uint16_t)) / (1024.0 * 1024.0));
+    (float) (ImageBufferSize() * Channels() + pixel_count * sizeof(uint16_t)) / (1024.0 * 1024.0),
+    (float) (ImageBufferSize() * Channels() + pixel_count * sizeof(uint16_t)) / (1024.0 * 1024.0));
   for (int i = 0; i < g.gpus; i++) {
     buddha_params p = g.params;
     p.device = g.params.device + i;
