@@ -25,7 +25,8 @@ import tempfile
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+# stdout carries exactly one JSON line: NCCL's own debug output goes to stderr, and so does
+# anything else a library writes to file descriptor 1 (see claim_stdout)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -64,6 +65,26 @@ METRIC = "candidate samples/sec"
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+_json_out = None
+
+
+def claim_stdout():
+    """Keep the real stdout for the one JSON line and point file descriptor 1 at stderr, so that C
+    libraries printing to stdout (NCCL's version banner under NCCL_DEBUG=VERSION) cannot get in
+    front of it."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 class ClockSampler:
@@ -221,7 +242,7 @@ def reference_arm(args, wl, rank):
                 "data": "synthetic", "impl": "reference", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -423,7 +444,7 @@ def native_arm(args, wl, rank, world, local_rank):
                                               "workload, this GPU, -t 5 (one run per channel)"}
     else:
         r.close()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -444,6 +465,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    if not (args.impl != "reference" and world != args.gpus and world == 1 and args.gpus > 1):
+        claim_stdout()  # (not in the parent that only re-launches itself under torchrun)
     if args.impl == "reference":
         return reference_arm(args, wl, rank)
     if world != args.gpus and world == 1 and args.gpus > 1:
