@@ -336,8 +336,11 @@ def native_arm(args, wl, rank, world, local_rank):
     # sanity: the merged histogram holds exactly the increments all ranks counted
     if rank == 0:
         merged_sum = int(hist_t.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum())
-        if merged_sum != increments_total:
-            raise RuntimeError("histogram sum %d != increments %d" % (merged_sum, increments_total))
+        # (fused contexts keep one device histogram per band: every in-canvas point is one cell
+        # increment there, cnt["increments"]; the per-channel sum increments_total counts a point
+        # once per accepting channel)
+        if merged_sum != cnt["increments"]:
+            raise RuntimeError("histogram sum %d != increments %d" % (merged_sum, cnt["increments"]))
 
     # ---- e2e: the same steps through the C ABI with HOST buffers ---------------------------
     # per step: H2D of the in-progress histogram (the -s buffer, cudabrot.cu:256), render, D2H of
@@ -423,11 +426,11 @@ def native_arm(args, wl, rank, world, local_rank):
     }
 
     # second roofline: red.global.add.u32 rate vs a probe scattering over the same footprint
-    red_peak = r.probe_red_peak(cells * 4)
+    red_peak = r.probe_red_peak(hist_t.numel() * 4)
     line["roofline_red"] = {
-        "bound": "l2-red", "unit": "Gred/s", "achieved": increments_total * scale / t_s / 1e9,
-        "peak": red_peak / 1e9, "frac": increments_total * scale / t_s / red_peak,
-        "footprint_bytes": cells * 4,
+        "bound": "l2-red", "unit": "Gred/s", "achieved": cnt["increments"] * scale / t_s / 1e9,
+        "peak": red_peak / 1e9, "frac": cnt["increments"] * scale / t_s / red_peak,
+        "footprint_bytes": hist_t.numel() * 4,
         "peak_source": "in-run probe: red.global.add.u32 to uniformly random cells of an array of "
                        "the histogram's size (buddha_probe_red_peak)",
         "algorithmic_bytes_per_increment": 4}

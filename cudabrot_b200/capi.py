@@ -30,7 +30,7 @@ EXPORTS = [
     "buddha_reset_counters", "buddha_tonemap_u16", "buddha_last_tonemap_ms",
     "buddha_device_histogram", "buddha_stream", "buddha_merge", "buddha_probe_fp64_peak",
     "buddha_probe_red_peak", "buddha_read_channel", "buddha_tonemap_channel_u16",
-    "buddha_get_channel_counters",
+    "buddha_get_channel_counters", "buddha_device_histogram_cells",
 ]
 MAX_CHANNELS = 4
 
@@ -121,6 +121,8 @@ def lib():
     L.buddha_last_tonemap_ms.argtypes = [ctx, C.POINTER(C.c_float)]
     L.buddha_device_histogram.argtypes = [ctx]
     L.buddha_device_histogram.restype = C.c_void_p
+    L.buddha_device_histogram_cells.argtypes = [ctx]
+    L.buddha_device_histogram_cells.restype = C.c_size_t
     L.buddha_stream.argtypes = [ctx]
     L.buddha_stream.restype = C.c_void_p
     L.buddha_merge.argtypes = [C.POINTER(ctx), C.c_int, C.c_int]

@@ -32,7 +32,7 @@ namespace {
 thread_local char g_create_error[512] = "";
 
 constexpr uint32_t kLutMax = 1u << 18;  // counts below this are tone-mapped through a full table
-constexpr int kTotalCnt = kCntSlots + kMaxChannels * kChSlots;  // common + per-channel accumulators
+constexpr int kTotalCnt = kCntSlots + kMaxBands * kChSlots;  // common + per-channel / per-band accumulators
 
 struct FastBin {
   double inv_half, c0_lo, c0_hi;
@@ -46,7 +46,11 @@ struct buddha_ctx {
   double delta_re, delta_im;
   size_t cells;                   // all channels
   size_t ch_cells;                // w * h
+  size_t dev_cells;               // cells of the device histogram: ch_cells x (bands, or 1)
   int n_ch;                       // 1, or the channels of a fused context
+  int n_bands;                    // fused: distinct channel sets along the step axis (RenderParams)
+  unsigned band_set[kMaxBands];   // fused: channels (bit k) of each band
+  uint32_t *d_preload;            // fused: counts given to buddha_load_histogram, [n_ch][h][w]
   int sm_count;
   int grid;                       // persistent grid: resident CTAs per SM x SMs
   int variant;                    // kernel instantiation: kVarShip | kVarFused
@@ -73,7 +77,7 @@ struct buddha_ctx {
   size_t pool_entries;
   double tile_pts_per_sample;
   uint16_t *d_gray;               // tone-mapped image, allocated on first use
-  uint32_t *d_chan;               // fused contexts: one de-interleaved channel, allocated on first use
+  uint32_t *d_chan;               // fused contexts: one assembled channel, allocated on first use
   uint16_t *d_lut;
   uint32_t *d_thr;
   uint32_t lut_capacity;
@@ -137,9 +141,41 @@ void fill_render_params(buddha_ctx *c) {
   r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
   r.ship = (p.flags & BUDDHA_F_BURNING_SHIP) ? 1 : 0;
   r.n_ch = c->n_ch > 1 ? c->n_ch : 0;
+  r.band_stride = (uint32_t)c->ch_cells;
+  if (c->n_ch > 1) {
+    // cut the escape-step axis (it = 1-based step of the escape; channel k takes
+    // channel_min[k] + 1 <= it <= channel_max[k]) at every window edge; each distinct non-empty
+    // set of accepting channels becomes a band
+    std::vector<long long> cuts;
+    for (int k = 0; k < c->n_ch; k++) {
+      cuts.push_back((long long)p.channel_min[k] + 1);
+      cuts.push_back((long long)p.channel_max[k] + 1);
+    }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    c->n_bands = 0;
+    r.n_seg = 0;
+    for (size_t i = 0; i + 1 < cuts.size(); i++) {
+      unsigned set = 0;
+      for (int k = 0; k < c->n_ch; k++)
+        if (cuts[i] >= (long long)p.channel_min[k] + 1 && cuts[i] <= (long long)p.channel_max[k])
+          set |= 1u << k;
+      int band = -1;
+      if (set) {
+        for (int b = 0; b < c->n_bands; b++) if (c->band_set[b] == set) band = b;
+        if (band < 0) { band = c->n_bands++; c->band_set[band] = set; }
+      }
+      const long long lo = std::max<long long>(cuts[i], -0x7fffffffLL);
+      r.seg_start[r.n_seg] = (int32_t)std::min<long long>(lo, 0x7fffffffLL);
+      r.seg_band[r.n_seg] = band;
+      r.n_seg++;
+    }
+    r.seg_start[r.n_seg] = (int32_t)std::min<long long>(cuts.back(), 0x7fffffffLL);
+    r.n_bands = c->n_bands;
+  }
   r.ch_low = p.max_iterations;
   for (int k = 0; k < c->n_ch && c->n_ch > 1; k++) {
-    r.ch_max[k] = p.channel_max[k]; r.ch_min[k] = p.channel_min[k];
+    r.ch_max[k] = p.channel_max[k];
     r.ch_low = std::min(r.ch_low, p.channel_max[k]);
   }
   uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
@@ -298,8 +334,11 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
                     kT2End, kOrbStepBits);
     if (p->flags & BUDDHA_F_SIMPLE_KERNEL)
       return fail(nullptr, BUDDHA_EINVAL, "the debug kernel renders one channel only");
-    if ((uint64_t)p->width * (uint64_t)p->height * (uint64_t)n_ch > 0xffffffffull)
-      return fail(nullptr, BUDDHA_EINVAL, "n_channels*width*height exceeds 2^32-1 cells");
+    for (int k = 0; k < n_ch; k++)
+      if (p->channel_min[k] < 0 || p->channel_min[k] >= p->channel_max[k])
+        return fail(nullptr, BUDDHA_EINVAL, "channel %d: need 0 <= min < max iterations", k);
+    if ((uint64_t)p->width * (uint64_t)p->height * (uint64_t)kMaxBands > 0xffffffffull)
+      return fail(nullptr, BUDDHA_EINVAL, "width*height too large for a fused context");
   }
 
   buddha_ctx *c = (buddha_ctx *)calloc(1, sizeof(buddha_ctx));
@@ -317,6 +356,7 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   c->n_ch = n_ch;
   c->ch_cells = (size_t)p->width * (size_t)p->height;
   c->cells = c->ch_cells * (size_t)n_ch;
+  c->n_bands = 0;
   c->sm_count = prop.multiProcessorCount;
   fill_render_params(c);
 
@@ -361,8 +401,9 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaEventCreate(&c->ev_b));
   CUC(cudaEventCreate(&c->ev_ta));
   CUC(cudaEventCreate(&c->ev_tb));
-  CUC(cudaMalloc(&c->d_hist, c->cells * sizeof(uint32_t)));
-  CUC(cudaMemsetAsync(c->d_hist, 0, c->cells * sizeof(uint32_t), c->stream));
+  c->dev_cells = c->ch_cells * (size_t)(n_ch > 1 ? c->n_bands : 1);
+  CUC(cudaMalloc(&c->d_hist, c->dev_cells * sizeof(uint32_t)));
+  CUC(cudaMemsetAsync(c->d_hist, 0, c->dev_cells * sizeof(uint32_t), c->stream));
   CUC(cudaMalloc(&c->d_cursor, sizeof(unsigned long long)));
   CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kTotalCnt));
   CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kTotalCnt, c->stream));
@@ -382,14 +423,15 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
     if ((e = getenv("BUDDHA_TILE_MIN_MB"))) min_mb = (size_t)strtoull(e, nullptr, 10);
     const bool forced = (p->flags & BUDDHA_F_FORCE_TILED) != 0;
     c->tiled = !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
-               (forced || c->cells * sizeof(uint32_t) >= (min_mb << 20));
+               (forced || c->dev_cells * sizeof(uint32_t) >= (min_mb << 20));
     if (c->tiled) {
       c->tile_shift = forced ? 12 : 24;  // 16 KB test tiles / 64 MB production tiles
       if ((e = getenv("BUDDHA_TILE_SHIFT"))) c->tile_shift = atoi(e);
       if (c->tile_shift < 8 || c->tile_shift > 28) c->tile_shift = 24;
-      // fused contexts count tiles in points of n_ch interleaved cells: keep the bytes per tile
-      if (n_ch > 1 && !forced) c->tile_shift -= (n_ch > 2) ? 2 : 1;
-      c->n_tiles = (int)((c->ch_cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
+      while (((c->dev_cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift) > 512 &&
+             c->tile_shift < 28)
+        c->tile_shift++;  // (the list table in shared memory holds at most 512 tiles)
+      c->n_tiles = (int)((c->dev_cells + ((size_t)1 << c->tile_shift) - 1) >> c->tile_shift);
       c->tile_smem = (size_t)c->n_tiles * kWarpsPerCta * sizeof(uint2);
       if (c->n_tiles > 512) {  // not a case tiling is meant for
         buddha_destroy(c);
@@ -449,6 +491,7 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->ev_applied[1]) cudaEventDestroy(c->ev_applied[1]);
   cudaFree(c->d_pool); cudaFree(c->d_tcount); cudaFree(c->d_tcap); cudaFree(c->d_tbase);
   cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr); cudaFree(c->d_chan);
+  cudaFree(c->d_preload);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_ta) cudaEventDestroy(c->ev_ta);
@@ -460,15 +503,30 @@ void buddha_destroy(buddha_ctx *c) {
 int buddha_clear_histogram(buddha_ctx *c) {
   if (!c) return BUDDHA_EINVAL;
   CU(c, cudaSetDevice(c->params.device));
-  CU(c, cudaMemsetAsync(c->d_hist, 0, c->cells * sizeof(uint32_t), c->stream));
+  CU(c, cudaMemsetAsync(c->d_hist, 0, c->dev_cells * sizeof(uint32_t), c->stream));
+  if (c->d_preload)
+    CU(c, cudaMemsetAsync(c->d_preload, 0, c->cells * sizeof(uint32_t), c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return BUDDHA_OK;
 }
 
-// Fused contexts keep the histogram interleaved on the device (uint32[h][w][n_ch]); the host API
-// is channel-major, so every transfer goes through one de-interleaved channel buffer.
+// Fused contexts keep one histogram per BAND on the device (RenderParams); the host API is
+// channel-major: a channel is assembled (sum of its bands + what was loaded) into one buffer.
 static int channel_buffer(buddha_ctx *c) {
   if (!c->d_chan) CU(c, cudaMalloc(&c->d_chan, sizeof(uint32_t) * c->ch_cells));
+  return BUDDHA_OK;
+}
+
+static int assemble_channel(buddha_ctx *c, int channel) {
+  int rc = channel_buffer(c);
+  if (rc) return rc;
+  unsigned bands = 0;
+  for (int b = 0; b < c->n_bands; b++)
+    if ((c->band_set[b] >> channel) & 1u) bands |= 1u << b;
+  channel_sum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
+      c->d_hist, c->d_preload ? c->d_preload + (size_t)channel * c->ch_cells : nullptr, c->d_chan,
+      c->ch_cells, bands);
+  CU(c, cudaGetLastError());
   return BUDDHA_OK;
 }
 
@@ -478,15 +536,11 @@ int buddha_load_histogram(buddha_ctx *c, const uint32_t *host, size_t cells) {
     return fail(c, BUDDHA_ESIZE, "histogram has %zu cells, canvas needs %zu", cells, c->cells);
   CU(c, cudaSetDevice(c->params.device));
   if (c->n_ch > 1) {
-    int rc = channel_buffer(c);
-    if (rc) return rc;
-    for (int k = 0; k < c->n_ch; k++) {
-      CU(c, cudaMemcpyAsync(c->d_chan, host + (size_t)k * c->ch_cells,
-                            c->ch_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-      channel_scatter_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
-                                                                     c->ch_cells, c->n_ch, k);
-      CU(c, cudaGetLastError());
-    }
+    // the loaded counts stay channel-major next to the (cleared) bands and are added on read
+    if (!c->d_preload) CU(c, cudaMalloc(&c->d_preload, sizeof(uint32_t) * c->cells));
+    CU(c, cudaMemsetAsync(c->d_hist, 0, c->dev_cells * sizeof(uint32_t), c->stream));
+    CU(c, cudaMemcpyAsync(c->d_preload, host, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                          c->stream));
   } else {
     CU(c, cudaMemcpyAsync(c->d_hist, host, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
                           c->stream));
@@ -503,11 +557,8 @@ int buddha_read_channel(buddha_ctx *c, int channel, uint32_t *host, size_t cells
   CU(c, cudaSetDevice(c->params.device));
   const uint32_t *src = c->d_hist;
   if (c->n_ch > 1) {
-    int rc = channel_buffer(c);
+    int rc = assemble_channel(c, channel);
     if (rc) return rc;
-    channel_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
-                                                                  c->ch_cells, c->n_ch, channel);
-    CU(c, cudaGetLastError());
     src = c->d_chan;
   }
   CU(c, cudaMemcpyAsync(host, src, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -591,8 +642,7 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       const int agrid = (int)((c->tile_warps + kApplyWarps - 1) / kApplyWarps);
       for (int t = 0; t < c->n_tiles; t++)
         apply_tile_kernel<<<agrid, kApplyWarps * 32, 0, side>>>(
-            c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift,
-            rp.n_ch);
+            c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift);
       CU(c, cudaEventRecord(c->ev_applied[b], side));
       c->apply_pending[b] = true;
       c->tile_buf = b ^ 1;
@@ -758,7 +808,13 @@ int buddha_get_channel_counters(buddha_ctx *c, int channel, buddha_counters *out
   unsigned long long v[kTotalCnt];
   int rc = read_counters(c, v);
   if (rc) return rc;
-  const unsigned long long *ch = v + kCntSlots + channel * kChSlots;
+  const unsigned long long *ch = v + kCntSlots + channel * kChSlots;  // kChHit / kChOver: by channel
+  unsigned long long accepted = 0, points = 0, increments = 0;       // the rest: by band
+  for (int b = 0; b < c->n_bands; b++) {
+    if (!((c->band_set[b] >> channel) & 1u)) continue;
+    const unsigned long long *bd = v + kCntSlots + b * kChSlots;
+    accepted += bd[kChAccepted]; points += bd[kChPoints]; increments += bd[kChIncrements];
+  }
   memset(out, 0, sizeof(*out));
   out->candidates = c->candidates;
   out->rejected = v[kCntRejected];
@@ -767,12 +823,12 @@ int buddha_get_channel_counters(buddha_ctx *c, int channel, buddha_counters *out
   const unsigned long long widest = (unsigned long long)c->params.max_iterations;
   const unsigned long long limit = (unsigned long long)c->params.channel_max[channel];
   out->hit_max = ch[kChHit] + v[kCntHitMax];
-  out->accepted = ch[kChAccepted];
-  out->too_early = c->candidates - v[kCntRejected] - out->hit_max - ch[kChAccepted];
+  out->accepted = accepted;
+  out->too_early = c->candidates - v[kCntRejected] - out->hit_max - accepted;
   // sum over samples of min(steps run, this channel's limit)
   out->escape_iters = v[kCntEscapeIters] - ch[kChOver] - v[kCntHitMax] * (widest - limit);
-  out->orbit_points = ch[kChPoints];
-  out->increments = ch[kChIncrements];
+  out->orbit_points = points;
+  out->increments = increments;
   out->executed_iters = v[kCntExecuted];
   out->shortcut_hits = v[kCntShortcut];
   out->exact_bins = v[kCntExactBins];
@@ -826,11 +882,8 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
     return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->ch_cells);
   const uint32_t *d_src = c->d_hist;
   if (c->n_ch > 1) {
-    int rc = channel_buffer(c);
+    int rc = assemble_channel(c, channel);
     if (rc) return rc;
-    channel_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_hist, c->d_chan,
-                                                                  c->ch_cells, c->n_ch, channel);
-    CU(c, cudaGetLastError());
     d_src = c->d_chan;
   }
   CU(c, cudaSetDevice(c->params.device));
@@ -924,6 +977,7 @@ int buddha_last_tonemap_ms(buddha_ctx *c, float *ms) {
 }
 
 void *buddha_device_histogram(buddha_ctx *c) { return c ? (void *)c->d_hist : nullptr; }
+size_t buddha_device_histogram_cells(buddha_ctx *c) { return c ? c->dev_cells : 0; }
 void *buddha_stream(buddha_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int buddha_merge(buddha_ctx **ctxs, int n, int root) {
@@ -932,7 +986,7 @@ int buddha_merge(buddha_ctx **ctxs, int n, int root) {
   buddha_ctx *r = ctxs[root];
   for (int i = 0; i < n; i++) {
     if (!ctxs[i]) return BUDDHA_EINVAL;
-    if (ctxs[i]->cells != r->cells) return fail(r, BUDDHA_ESIZE, "contexts differ in canvas size");
+    if (ctxs[i]->dev_cells != r->dev_cells) return fail(r, BUDDHA_ESIZE, "contexts differ in canvas size");
   }
   NcclApi *nccl = load_nccl();
   if (!nccl) return fail(r, BUDDHA_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
@@ -945,7 +999,7 @@ int buddha_merge(buddha_ctx **ctxs, int n, int root) {
   rc = nccl->GroupStart();
   for (int i = 0; i < n && !rc; i++) {
     cudaSetDevice(devs[i]);
-    rc = nccl->Reduce(ctxs[i]->d_hist, ctxs[i]->d_hist, r->cells, /*ncclUint32*/ 3, /*ncclSum*/ 0,
+    rc = nccl->Reduce(ctxs[i]->d_hist, ctxs[i]->d_hist, r->dev_cells, /*ncclUint32*/ 3, /*ncclSum*/ 0,
                       root, comms[i], ctxs[i]->stream);
   }
   int rc2 = nccl->GroupEnd();

@@ -38,7 +38,8 @@ constexpr int kOrbExit = 28;                   // (tier ends, kBlock and the two
                                                //  profiles/r01_summary.md)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxChannels = 4;                // fused multi-channel render
-constexpr int kOrbStepBits = 28;               // fused: orbit entries carry (mask << 28) | steps
+constexpr int kMaxBands = 2 * kMaxChannels - 1;  // distinct channel sets along the escape-step axis
+constexpr int kOrbStepBits = 28;               // fused: orbit entries carry (band << 28) | steps
 
 // Fast binning: T = fma(X, inv_half, C0) lands in [1.5*2^40, 1.5*2^40 + 2^20) for in-range
 // quotients, where the low mantissa word holds quotient * 2^12.
@@ -49,7 +50,8 @@ enum CounterSlot {
   kCntRejected = 0, kCntHitMax, kCntTooEarly, kCntAccepted, kCntEscapeIters, kCntOrbitPoints,
   kCntIncrements, kCntExecuted, kCntShortcut, kCntExactBins, kCntSlots
 };
-// fused render: per-channel accumulators follow the kCntSlots common ones, kChSlots per channel
+// fused render: accumulators that follow the kCntSlots common ones, kChSlots per index; kChHit and
+// kChOver are indexed by CHANNEL, the other three by BAND (see RenderParams)
 enum ChannelSlot { kChHit = 0, kChOver, kChAccepted, kChPoints, kChIncrements, kChSlots };
 
 struct RenderParams {
@@ -64,13 +66,19 @@ struct RenderParams {
   int32_t shortcut;
   int32_t ship;                 // burning-ship variant (only the simple kernel reads this at run time)
   // fused multi-channel render: channel k accepts a sample that escapes at step `it` iff
-  // ch_min[k] <= it - 1 < ch_max[k].  The device histogram is then INTERLEAVED, uint32[h][w][n_ch]:
-  // the (up to n_ch) increments of one orbit point fall into one 32-byte sector instead of n_ch
-  // sectors hundreds of MB apart (the host API transposes: its layout stays channel-major).
-  // max_it / min_it above are the largest ch_max / the smallest ch_min.
+  // ch_min[k] <= it - 1 < ch_max[k].  The channels' windows cut the step axis into segments with a
+  // constant set of accepting channels; each distinct non-empty set is a BAND with its own
+  // histogram (hist + band * band_stride), so every orbit point costs ONE increment however many
+  // channels take it, and channel k = the sum of the bands whose set contains k (formed when the
+  // channel is read; sums are mod 2^32 like the cells themselves).  max_it / min_it above are the
+  // largest ch_max / the smallest ch_min.
   int32_t n_ch;
-  int32_t ch_max[kMaxChannels], ch_min[kMaxChannels];
+  int32_t ch_max[kMaxChannels];
   int32_t ch_low;               // smallest ch_max: below it no channel has hit its limit yet
+  int32_t n_bands, n_seg;
+  int32_t seg_start[2 * kMaxChannels + 1];  // segment s covers steps seg_start[s] .. seg_start[s+1]-1
+  int32_t seg_band[2 * kMaxChannels];       // its band, or -1 if no channel accepts there
+  uint32_t band_stride;         // cells per band (= w * h)
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
   uint32_t chunk;               // sample indices a warp takes per cursor grab (multiple of 32):
@@ -189,25 +197,6 @@ __device__ __forceinline__ void scatter(const RenderParams &p, const Sink &k, ui
     }
   }
   red_add_u32(k.hist + idx);
-}
-
-// Fused render: one orbit point, `mask` = the channels that take it.  Tiles are counted in POINTS
-// (a tile holds 2^tile_shift points = n_ch << tile_shift cells) and a list entry carries the mask
-// above the tile-local point offset, so a point costs one append however many channels take it.
-__device__ __forceinline__ void scatter_fused(const RenderParams &p, const Sink &k, uint32_t idx,
-                                              unsigned mask) {
-  if (p.tile_shift) {
-    uint2 *e = k.tile_tab + (idx >> p.tile_shift);
-    const uint32_t slot = atomicAdd(&e->x, 1u);
-    if (slot < e->y) {
-      __stcs(p.pool + slot, (idx & ((1u << p.tile_shift) - 1u)) | (mask << kOrbStepBits));
-      return;
-    }
-  }
-  uint32_t *cell = k.hist + (size_t)idx * (uint32_t)p.n_ch;
-#pragma unroll
-  for (int c = 0; c < kMaxChannels; c++)
-    if ((mask >> c) & 1u) red_add_u32(cell + c);
 }
 
 // Per-warp list table: set it up (mode 0: empty lists, mode 1: continue where an earlier kernel
@@ -386,7 +375,7 @@ struct WarpState {
   uint32_t skipped;    // iterations the periodicity shortcut did not have to run (escape_iters only)
   uint32_t wasted;     // deep rounds that were rolled back (executed only)
   uint32_t p_pts, p_inc;
-  uint32_t ch_inc[kMaxChannels];  // fused render only: increments per channel
+  uint32_t ch_inc[kMaxBands];     // fused render only: increments per band
 };
 
 // Warp-reduce nine per-lane counters and add them to the global accumulators.  Deliberately not
@@ -429,8 +418,8 @@ __device__ __forceinline__ void flush_channel_counters(const RenderParams &p, Wa
                                                        unsigned long long *counters) {
   if constexpr ((kVar & kVarFused) != 0) {
 #pragma unroll
-    for (int k = 0; k < kMaxChannels; k++) {
-      if (k < p.n_ch) channel_add(counters, k, kChIncrements, ws.ch_inc[k]);
+    for (int k = 0; k < kMaxBands; k++) {
+      if (k < p.n_bands) channel_add(counters, k, kChIncrements, ws.ch_inc[k]);
       ws.ch_inc[k] = 0;
     }
   }
@@ -450,27 +439,28 @@ __device__ __forceinline__ void push_z(ZStack &st, int &height, bool pred, doubl
   if (pred) { st.c[slot] = make_double2(cx, cy); st.z[slot] = make_double2(x, y); st.it[slot] = it; }
 }
 
-// Channels (bit k) whose window accepts an escape at step `it` (1-based count, it <= max_it).
-__device__ __forceinline__ unsigned accept_mask(const RenderParams &p, int it) {
-  unsigned m = 0;
+// Band (+1; 0 = no channel) that an escape at step `it` (1-based count, it <= max_it) falls into.
+__device__ __forceinline__ unsigned accept_band(const RenderParams &p, int it) {
+  unsigned code = 0;
 #pragma unroll
-  for (int k = 0; k < kMaxChannels; k++)
-    if (k < p.n_ch && it - 1 >= p.ch_min[k] && it <= p.ch_max[k]) m |= 1u << k;
-  return m;
+  for (int s = 0; s < 2 * kMaxChannels; s++)
+    if (s < p.n_seg && it >= p.seg_start[s] && it < p.seg_start[s + 1])
+      code = (unsigned)(p.seg_band[s] + 1);
+  return code;
 }
 
 // The accept filter (cudabrot.cu:407-408) for lanes whose sample escaped at step `it`, and the
-// push of the accepted ones.  Fused render: a sample is pushed if any channel accepts it; the
-// channel mask travels in the top bits of the step count.
+// push of the accepted ones.  Fused render: a sample is pushed if any channel accepts it; its
+// band travels in the top bits of the step count.
 template <int kVar>
 __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            unsigned long long *counters, bool esc, double cx,
                                            double cy, int it) {
-  unsigned mask = 0;
+  unsigned code = 0;  // band + 1
   bool acc;
   if constexpr ((kVar & kVarFused) != 0) {
-    mask = esc ? accept_mask(p, it) : 0u;
-    acc = mask != 0u;
+    code = esc ? accept_band(p, it) : 0u;
+    acc = code != 0u;
   } else {
     acc = esc && it - 1 >= p.min_it;
   }
@@ -480,15 +470,15 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
   if (__ballot_sync(kFull, (ws.p_pts >> 30) != 0u)) flush_counters(ws, counters);  // (huge -m)
   int n = it;
   if constexpr ((kVar & kVarFused) != 0) {
-    for (int k = 0; k < p.n_ch; k++) {
-      const bool a = (mask >> k) & 1u;
+    for (int k = 0; k < p.n_bands; k++) {
+      const bool a = code == (unsigned)(k + 1);
       const unsigned n = __popc(__ballot_sync(kFull, a));
       if (n == 0u) continue;
       if (lane_id() == 0)
         atomicAdd(counters + kCntSlots + k * kChSlots + kChAccepted, (unsigned long long)n);
       channel_add(counters, k, kChPoints, a ? (uint32_t)it : 0u);
     }
-    n |= (int)(mask << kOrbStepBits);
+    n |= (int)((code - 1u) << kOrbStepBits);
   }
   push_z(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
 }
@@ -549,7 +539,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
         uint32_t any = ws.n_rej | ws.n_hit | ws.n_acc | ws.n_cyc | ws.n_exact | ws.steps |
                        ws.skipped | ws.wasted | ws.p_pts | ws.p_inc;
 #pragma unroll
-        for (int k = 0; k < kMaxChannels; k++) any |= ws.ch_inc[k];
+        for (int k = 0; k < kMaxBands; k++) any |= ws.ch_inc[k];
         if (__ballot_sync(kFull, (any >> 29) != 0u)) {
           flush_counters(ws, counters);
           flush_channel_counters<kVar>(p, ws, counters);
@@ -796,8 +786,8 @@ struct OrbitLane {
 // bin_exact_index.  The common path is branch-free (the increment is a predicated reduction), so
 // the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
 // the rare exact-binning case branches.
-// (fused render: o.n carries the channel mask above bit kOrbStepBits; the point goes to every
-// accepting channel's histogram)
+// (fused render: o.n carries the band above bit kOrbStepBits; the point goes to that band's
+// histogram)
 template <int kVar>
 __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                           const Sink &hist) {
@@ -824,7 +814,7 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, W
       in = bin_exact_index(o.x, o.y, p, &idx);
     }
     o.inc += in ? 1u : 0u;
-    if (in) scatter_fused(p, hist, idx, (unsigned)o.n >> kOrbStepBits);
+    if (in) scatter(p, hist, idx + ((unsigned)o.n >> kOrbStepBits) * p.band_stride);
   } else {
     if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
     ws.p_inc += hit ? 1u : 0u;
@@ -835,15 +825,15 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, W
   }
 }
 
-// Fused render: credit the in-canvas points an orbit has collected to the channels in its mask
-// (per orbit, not per point).  Call before o.n is overwritten or given away.
+// Fused render: credit the in-canvas points an orbit has collected to its band (per orbit, not
+// per point).  Call before o.n is overwritten or given away.
 template <int kVar>
 __device__ __forceinline__ void orbit_credit(OrbitLane &o, WarpState &ws) {
   if constexpr ((kVar & kVarFused) != 0) {
-    const unsigned mask = (unsigned)o.n >> kOrbStepBits;
+    const unsigned band = (unsigned)o.n >> kOrbStepBits;
     ws.p_inc += o.inc;
 #pragma unroll
-    for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] += ((mask >> k) & 1u) ? o.inc : 0u;
+    for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] += (band == (unsigned)k) ? o.inc : 0u;
     o.inc = 0;
   }
 }
@@ -917,7 +907,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 #pragma unroll
-  for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] = 0;
+  for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
 #pragma unroll 1
   for (;;) {
@@ -988,7 +978,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
   ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
 #pragma unroll
-  for (int k = 0; k < kMaxChannels; k++) ws.ch_inc[k] = 0;
+  for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
   int g = 32;
   {
@@ -1001,7 +991,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   const int sub = lane & (g - 1), leader = lane & ~(g - 1);
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
   int n = 0;          // steps this group's orbit still has to record (group-uniform)
-  unsigned mask = 0;  // fused render: the channels that accepted it
+  unsigned mask = 0;  // fused render: its band
   bool more = true;   // the list may still hold entries (group-uniform)
 #pragma unroll 1
   for (;;) {
@@ -1048,27 +1038,14 @@ constexpr int kApplyWarps = 4;
 __global__ void __launch_bounds__(kApplyWarps * 32)
 apply_tile_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ tcount,
                   const uint32_t *__restrict__ tile_cap, const uint32_t *__restrict__ tile_base,
-                  const uint32_t *__restrict__ pool, int t, uint32_t n_warps, int tile_shift,
-                  int n_ch) {
+                  const uint32_t *__restrict__ pool, int t, uint32_t n_warps, int tile_shift) {
   const uint32_t w = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
   if (w >= n_warps) return;
   const uint32_t cap = tile_cap[t];
   const uint32_t n = min(tcount[(size_t)t * n_warps + w], cap);
   const uint32_t *src = pool + (tile_base[t] + w * cap);
-  uint32_t i = lane_id();
-  if (n_ch) {
-    // fused render: entry = tile-local point | channel mask << 28; the point's cells are adjacent
-    uint32_t *tile = hist + ((size_t)t << tile_shift) * (uint32_t)n_ch;
-    for (; i < n; i += 32) {
-      const uint32_t e = __ldcs(src + i);
-      uint32_t *cell = tile + (size_t)(e & ((1u << kOrbStepBits) - 1u)) * (uint32_t)n_ch;
-#pragma unroll
-      for (int c = 0; c < kMaxChannels; c++)
-        if ((e >> (kOrbStepBits + c)) & 1u) red_add_u32(cell + c);
-    }
-    return;
-  }
   uint32_t *tile = hist + ((size_t)t << tile_shift);
+  uint32_t i = lane_id();
   for (; i + 96 < n; i += 128) {
     uint32_t a = __ldcs(src + i), b = __ldcs(src + i + 32), c = __ldcs(src + i + 64),
              d = __ldcs(src + i + 96);
@@ -1077,21 +1054,19 @@ apply_tile_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ tcou
   for (; i < n; i += 32) red_add_u32(tile + __ldcs(src + i));
 }
 
-// Channel <-> interleaved layout of a fused context: out[i] = hist[i * n_ch + ch] and back.
+// Fused contexts: channel = sum of the bands in `bands` (bit b = band b) plus, if given, the
+// channel's preloaded counts (buddha_load_histogram); mod 2^32 like the cells themselves.
 __global__ void __launch_bounds__(256)
-channel_gather_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ out, size_t cells,
-                      int n_ch, int ch) {
+channel_sum_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ preload,
+                   uint32_t *__restrict__ out, size_t cells, unsigned bands) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
-    out[i] = hist[i * (size_t)n_ch + ch];
-}
-
-__global__ void __launch_bounds__(256)
-channel_scatter_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ in, size_t cells,
-                       int n_ch, int ch) {
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
-    hist[i * (size_t)n_ch + ch] = in[i];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+    uint32_t v = preload ? preload[i] : 0u;
+#pragma unroll
+    for (int b = 0; b < kMaxBands; b++)
+      if ((bands >> b) & 1u) v += hist[(size_t)b * cells + i];
+    out[i] = v;
+  }
 }
 
 // ---- tone-map (cudabrot.cu:416-468) ----------------------------------------------------------

@@ -155,7 +155,8 @@ class Renderer:
 
         a = _Alias()
         a.__cuda_array_interface__ = {
-            "shape": (self.cells,), "typestr": "<i4", "data": (self.device_histogram_ptr, False),
+            "shape": (int(self._lib.buddha_device_histogram_cells(self._ctx)),), "typestr": "<i4",
+            "data": (self.device_histogram_ptr, False),
             "version": 2, "strides": None,
         }
         return torch.as_tensor(a, device="cuda:%d" % self.params.device)

@@ -60,8 +60,8 @@ typedef struct {
    * the reference once per colour channel).  n_channels >= 2 renders every candidate ONCE and adds
    * its orbit to each channel k whose window channel_min[k] <= i < channel_max[k] accepts it;
    * max_iterations / min_iterations above are then ignored.  The histogram becomes
-   * uint32[n_channels][h][w] at this API (on the device it is interleaved, uint32[h][w][n_channels],
-   * which is what buddha_device_histogram points to); channel k is bit-identical to what a single-channel context with
+   * uint32[n_channels][h][w] at this API (on the device it is one histogram per distinct set of
+   * accepting channels, which is what buddha_device_histogram points to); channel k is bit-identical to what a single-channel context with
    * (-m channel_max[k], -c channel_min[k]) renders from the same sample indices.  Every
    * channel_max must be > 22 and < 2^28.  0 or 1 = the plain single-channel render. */
   uint32_t n_channels;
@@ -173,6 +173,8 @@ int buddha_last_tonemap_ms(buddha_ctx *ctx, float *ms);
  * Raw device pointer + CUDA stream of this context, so a host framework (torch.distributed / NCCL)
  * can reduce the private histograms in place. */
 void *buddha_device_histogram(buddha_ctx *ctx);
+/* Cells behind that pointer: w*h, or for a fused context w*h times its number of bands. */
+size_t buddha_device_histogram_cells(buddha_ctx *ctx);
 void *buddha_stream(buddha_ctx *ctx);
 
 /* In-process merge: sums the histograms of n contexts (one per GPU) into ctxs[root] with a single
