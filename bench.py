@@ -197,6 +197,16 @@ def run_reference_binary(wl, seconds, device=0):
         return passes * REFERENCE_PASS / secs, passes, secs
 
 
+def make_config(name, wl):
+    """The same dict for both arms (the driver compares them)."""
+    w, h, m, c, canvas, _ = wl
+    return {"workload": "%s: %dx%d canvas %s, max-iter %d, min-cutoff %d" %
+            (name, w, h, list(canvas), m, c), "seed": 1337,
+            "l2": "cold between timed steps (native arm: 256 MiB flush write; reference arm: one "
+                  "process per step)",
+            "inputs": "candidate samples are drawn on the device (Philox / the reference's XORWOW)"}
+
+
 def reference_arm(args, wl, rank):
     """--impl reference: rank 0 alone runs and prints; other ranks exit 0."""
     if rank != 0:
@@ -211,8 +221,7 @@ def reference_arm(args, wl, rank):
             break
         if i >= args.warmup:
             runs.append(r)
-    config = {"workload": "%s: %dx%d canvas %s, max-iter %d, min-cutoff %d" %
-              (args.workload, w, h, list(canvas), m, c), "seed": 1337}
+    config = make_config(args.workload, wl)
     if runs:
         samples = sum(r[1] for r in runs) * REFERENCE_PASS
         t = sum(r[2] for r in runs)
@@ -246,54 +255,216 @@ def reference_arm(args, wl, rank):
     return 0
 
 
-def native_arm(args, wl, rank, world, local_rank):
+# ---- roofline model --------------------------------------------------------------------------
+# FP64-pipe warp instructions the render kernel EXECUTES, as lane-instructions per unit of work,
+# calibrated against ncu (sm__inst_executed_pipe_fp64 of render_persistent_kernel, 2^30-sample
+# launches, profiles/r02_render_cfg{1,2}_ncu_raw_selected.csv): a per candidate (Philox
+# coordinates 4, cardioid/bulb 9, two tested steps 14, plus the tiers' re-computed prefixes and
+# tested steps), b per escape-pass iteration actually executed (4 per unchecked deep step, 7 per
+# tested step, idle lanes and rolled-back rounds included), c per recorded orbit point (step 4 +
+# division-free binning 4, at the orbit phase's >= 87.5 % lane occupancy).
+FP64_MODEL = {"per_candidate": 34.7, "per_executed_iteration": 4.36, "per_orbit_point": 8.6}
+HW_FP64_LANES = 148 * 64  # FP64 lanes of one B200: the hardware issue rate is this x the SM clock
+
+
+def fp64_lane_instr(S, cnt, scale=1.0):
+    m = FP64_MODEL
+    return (m["per_candidate"] * S + m["per_executed_iteration"] * cnt["executed_iters"] * scale +
+            m["per_orbit_point"] * cnt["orbit_points"] * scale)
+
+
+def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload):
+    """roofline of the dominant kernel (render_persistent_kernel): executed FP64 lane-instructions
+    per second against the in-run DFMA probe; the reference-dataflow figure of SURVEY.md 8(d)
+    (14 S + 8 E + 8 P, with E what the reference would have to execute) is kept beside it."""
+    lane = fp64_lane_instr(S, cnt, scale)
+    lane_ref = 14 * S + 8 * cnt["escape_iters"] * scale + 8 * cnt["orbit_points"] * scale
+    hw = HW_FP64_LANES * (sm_mhz or 1965.0) * 1e6
+    return {
+        "bound": "fp64-pipe", "unit": "Tlane-instr/s",
+        "achieved": lane / t_s / 1e12, "peak": fp64_peak / 1e12, "frac": lane / t_s / fp64_peak,
+        "frac_of_hw_issue_rate": lane / t_s / hw,
+        "hw_issue_rate": hw / 1e12,
+        "traffic": NCU_DRAM_BYTES_PER_2P30_LAUNCH.get(workload),
+        "traffic_note": "DRAM bytes (read+write) of one render_persistent_kernel launch over 2^30 "
+                        "samples of this workload (ncu --set full, profiles/); algorithmic memory "
+                        "traffic is 4 B per in-canvas increment at L2",
+        "peak_source": "in-run independent-DFMA probe (buddha_probe_fp64_peak; reads ~92 % of "
+                       "148 SM x 64 lanes x SM clock = hw_issue_rate); MEASURED_PEAKS.json has no "
+                       "FP64 figure",
+        "numerator": "FP64-pipe lane-instructions the kernel executes: %.1f per candidate + %.2f "
+                     "per executed escape iteration + %.1f per orbit point (ncu-calibrated, "
+                     "bench.py FP64_MODEL)" % (FP64_MODEL["per_candidate"],
+                                                FP64_MODEL["per_executed_iteration"],
+                                                FP64_MODEL["per_orbit_point"]),
+        "frac_reference_dataflow": lane_ref / t_s / fp64_peak,
+        "reference_dataflow_note": "14 S + 8 E + 8 P with E = the iterations the REFERENCE must run "
+                                   "for the same output (SURVEY.md 8(d)); a speed-up factor of the "
+                                   "exact periodicity shortcut and the 4-instruction step, not a "
+                                   "utilisation",
+    }
+
+
+def make_red_roofline(r, cnt, scale, t_s, hist_bytes, tiled, workload):
+    """Second bound: the histogram reductions.  Direct scatter: the probe's random
+    red.global.add.u32 rate over a footprint of the histogram's size.  Tiled scatter (histograms far
+    beyond L2): every increment is appended to a list (4 B written, 4 B read back) and applied as a
+    reduction inside an L2-resident 64 MB tile, so the ceiling is the in-L2 reduction rate."""
+    inc = cnt["increments"] * scale
+    foot = min(hist_bytes, 64 << 20) if tiled else hist_bytes
+    peak = r.probe_red_peak(foot)
+    out = {"bound": "l2-red", "unit": "Gred/s", "achieved": inc / t_s / 1e9, "peak": peak / 1e9,
+           "frac": inc / t_s / peak, "footprint_bytes": hist_bytes, "tiled_scatter": bool(tiled),
+           "peak_source": "in-run probe: red.global.add.u32 to uniformly random cells of a %d MB "
+                          "array (%s)" % (foot >> 20, "one L2-resident tile" if tiled else
+                                          "the histogram's size"),
+           "algorithmic_bytes_per_increment": 4}
+    if tiled:
+        # HBM bytes the tiled pipeline has to move: the list entry written and read back (8 B per
+        # increment) plus one read and one write-back of every 64 MB tile per pipeline launch
+        # (a launch = 1 render + 1 drain + n_tiles apply kernels)
+        n_tiles = -(-hist_bytes // (64 << 20))
+        launches = max(cnt["kernel_launches"] * scale / (2 + n_tiles), 1.0)
+        model = 8.0 * inc + 2.0 * hist_bytes * launches
+        out["hbm_model_bytes_per_increment"] = model / max(inc, 1.0)
+        out["hbm_model_gbs"] = model / t_s / 1e9
+        out["hbm_model"] = "4 B list write + 4 B list read per increment, plus one read and one " \
+                           "write-back of each 64 MB tile per pipeline launch; 4 B algorithmic"
+        dram = NCU_DRAM_BYTES_PER_2P30_LAUNCH.get(workload)
+        if dram:
+            out["ncu_dram_bytes_per_2p30_launch"] = dram
+    return out
+
+
+def e2e_pipeline(r, ranges, host_in, host_hist, host_img, n_ch, shape, rank, world, hist_t, dist):
+    """The job through the public C ABI with HOST buffers, copies overlapped with rendering
+    (buddha.h "Overlapped host transfers").  Per step: the saved in-progress counts go in
+    (buddha_add_histogram_async, H2D from pinned memory, root only), every rank renders its range,
+    N > 1: one reduce(sum) to the root and the others start from zero again, the root freezes the
+    result (buddha_snapshot) and reads histogram + 16-bit image of step k-1 back (D2H) while step k
+    renders.  Returns wall seconds (caller brackets with barriers)."""
+    import torch
+    h, w = shape
+    t0 = time.perf_counter()
+    pending = False
+    for (f, n) in ranges:
+        if rank == 0:
+            r.add_histogram_async(host_in)
+        r.render_samples_async(f, n)
+        if rank == 0 and pending:
+            r.read_snapshot(host_hist)
+            for ch in range(n_ch):
+                r.tonemap_snapshot(1.0, True, out=host_img.reshape(n_ch, h, w)[ch], channel=ch)
+        r.sync()
+        if world > 1:
+            dist.reduce(hist_t, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            if rank != 0:
+                r.clear()
+        if rank == 0:
+            r.snapshot()
+            pending = True
+    if rank == 0 and pending:
+        r.read_snapshot(host_hist)
+        for ch in range(n_ch):
+            r.tonemap_snapshot(1.0, True, out=host_img.reshape(n_ch, h, w)[ch], channel=ch)
+    r.sync()
+    return time.perf_counter() - t0
+
+
+def pinned(n, dtype):
     import numpy as np
     import torch
-    import torch.distributed as dist
-    import cudabrot_b200 as B
-    from cudabrot_b200.sharding import merge_to_root, step_range
+    tdt = {"uint32": torch.int32, "uint16": torch.int16}[dtype]
+    return torch.zeros(n, dtype=tdt).pin_memory().numpy().view(getattr(np, dtype))
 
-    w, h, m, c, canvas, default_step = wl
-    per_gpu = args.samples_per_step or default_step
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    flags = B.F_NO_SHORTCUT if args.no_shortcut else 0
-    channels = CHANNELS.get(args.workload)
-    r = B.Renderer(w, h, m, c, canvas=canvas, seed=1337, device=local_rank, flags=flags,
+
+class Ctx:
+    """What every part of the native arm needs."""
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.torch, self.dist = torch, dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def allsum_counters(self, cnt, extra=()):
+        keys = ["rejected", "hit_max", "too_early", "accepted", "escape_iters", "orbit_points",
+                "increments", "executed_iters", "shortcut_hits", "kernel_launches", "exact_bins"]
+        vals = [cnt[k] for k in keys] + list(extra)
+        if self.world > 1:
+            t = self.torch.tensor(vals, dtype=self.torch.int64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            vals = t.tolist()
+        out = dict(cnt)
+        out.update(zip(keys, vals[:len(keys)]))
+        return out, vals[len(keys):]
+
+    def bcast_int(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device="cuda")
+        self.dist.broadcast(t, src=0)
+        return int(t[0])
+
+
+def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=None,
+                 baselines=False):
+    """Weak-scaling run of one BASELINE workload: every (step, rank) renders a fresh block of
+    `per_gpu` sample indices; device-timed per step with an L2 flush in between; then the e2e
+    pipeline.  steps = 0: as many steps as `min_seconds` of device time need.  Returns the result
+    dict on rank 0 (None elsewhere)."""
+    import numpy as np
+    import cudabrot_b200 as B
+    from cudabrot_b200.sharding import step_range
+    torch, dist = cx.torch, cx.dist
+    rank, world = cx.rank, cx.world
+    w, h, m, c, canvas, _ = WORKLOADS[name]
+    channels = CHANNELS.get(name)
+    flags = B.F_NO_SHORTCUT if cx.args.no_shortcut else 0
+    r = B.Renderer(w, h, m, c, canvas=canvas, seed=1337, device=cx.local_rank, flags=flags,
                    channels=channels)
     n_ch = len(channels) if channels else 1
     cells = w * h * n_ch
     hist_t = r.histogram_as_tensor()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    hist_bytes = hist_t.numel() * 4
+    tiled = hist_bytes >= (640 << 20)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-
-    # ---- warm-up (untimed), incl. one collective so NCCL is initialised -------------------
-    for k in range(args.warmup):
-        f, n = step_range(k, rank, world, per_gpu, first=1 << 56)
+    # ---- warm-up (untimed): also calibrates the tile lists of a tiled context ----------------
+    for k in range(max(warmup, 1)):
+        f, n = step_range(k, rank, world, min(per_gpu, 1 << 32) if steps == 0 else per_gpu,
+                          first=1 << 56)
         r.render_samples(f, n)
-    if world > 1:
-        tmp = torch.zeros(1024, dtype=torch.int32, device="cuda")
-        merge_to_root(tmp)
+        t_first = r.last_render_ms() * per_gpu / n
+    if steps == 0:
+        steps = cx.bcast_int(max(2, int(np.ceil(min_seconds * 1e3 / max(t_first, 1e-3)))))
     r.clear()
     r.reset_counters()
     fp64_peak = r.probe_fp64_peak()
 
-    # ---- timed region: K steps (+ the one merge), device-timed per step ---------------------
-    barrier()
+    sampler = ClockSampler(cx.local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)  # nvidia-smi needs a moment before its first line
+    # ---- timed region: `steps` steps, device-timed per step --------------------------------
+    cx.barrier()
     sampler.mark_start()
     wall0 = time.perf_counter()
     dev_ms = 0.0
-    for k in range(args.steps):
-        flush.zero_()                       # L2 flush between timed steps (not timed)
+    for k in range(steps):
+        cx.flush.zero_()                    # L2 flush between timed steps (not timed)
         torch.cuda.synchronize()
         f, n = step_range(k, rank, world, per_gpu)
         r.render_samples(f, n)
@@ -303,139 +474,241 @@ def native_arm(args, wl, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        merge_to_root(hist_t)               # the single collective: ncclReduce(sum) to rank 0
+        dist.reduce(hist_t, dst=0, op=dist.ReduceOp.SUM)   # the single collective: ncclReduce(sum)
         e1.record()
         torch.cuda.synchronize()
         merge_ms = e0.elapsed_time(e1)
-    barrier()
+    cx.barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     clocks = sampler.stop() if rank == 0 else None
-    cnt = r.counters()
-    # cells incremented: fused contexts add a point to every accepting channel
+    cnt_local = r.counters()
     inc_local = sum(r.channel_counters(k)["increments"] for k in range(n_ch)) if channels \
-        else cnt["increments"]
-    increments_total = inc_local
-
-    total_ms = dev_ms + merge_ms
-    if world > 1:
-        t = torch.tensor([total_ms, wall_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, wall_ms = float(t[0]), float(t[1])
-        keys = ["rejected", "hit_max", "too_early", "accepted", "escape_iters", "orbit_points",
-                "increments", "executed_iters", "shortcut_hits", "kernel_launches", "exact_bins"]
-        ct = torch.tensor([cnt[k] for k in keys], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ct, op=dist.ReduceOp.SUM)
-        for k, v in zip(keys, ct.tolist()):
-            cnt[k] = v
-        it = torch.tensor([inc_local], dtype=torch.int64, device="cuda")
-        dist.all_reduce(it, op=dist.ReduceOp.SUM)
-        increments_total = int(it[0])
-    samples_total = per_gpu * args.steps * world
+        else cnt_local["increments"]
+    total_ms, wall_ms, merge_max = cx.allmax(dev_ms + merge_ms, wall_ms, merge_ms)
+    cnt, (inc_total,) = cx.allsum_counters(cnt_local, extra=(inc_local,))
+    samples_total = per_gpu * steps * world
     value = samples_total / (total_ms * 1e-3)
-
-    # sanity: the merged histogram holds exactly the increments all ranks counted
     if rank == 0:
+        # sanity: the merged histogram holds exactly the increments all ranks counted (fused
+        # contexts keep one device histogram per band: one cell increment per in-canvas point)
         merged_sum = int(hist_t.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum())
-        # (fused contexts keep one device histogram per band: every in-canvas point is one cell
-        # increment there, cnt["increments"]; the per-channel sum increments_total counts a point
-        # once per accepting channel)
         if merged_sum != cnt["increments"]:
-            raise RuntimeError("histogram sum %d != increments %d" % (merged_sum, cnt["increments"]))
+            raise RuntimeError("%s: histogram sum %d != increments %d" %
+                               (name, merged_sum, cnt["increments"]))
 
-    # ---- e2e: the same steps through the C ABI with HOST buffers ---------------------------
-    # per step: H2D of the in-progress histogram (the -s buffer, cudabrot.cu:256), render, D2H of
-    # the histogram (:496) and the tone-mapped 16-bit image (:500); pinned host memory
-    host_hist = torch.zeros(cells, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    host_img = torch.zeros(cells, dtype=torch.int16).pin_memory().numpy().view(np.uint16)
-    barrier()
-    e2e_t0 = time.perf_counter()
-    for k in range(args.steps):
-        f, n = step_range(k, rank, world, per_gpu, first=1 << 57)
-        r.load_histogram(host_hist)
-        r.render_samples(f, n)
-        r.read_histogram(host_hist.reshape((n_ch, h, w) if channels else (h, w)))
-        for ch in range(n_ch):
-            r.tonemap(1.0, True, out=host_img.reshape(n_ch, h, w)[ch], channel=ch)
-    barrier()
-    e2e_s = time.perf_counter() - e2e_t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    e2e_value = samples_total / e2e_s
+    # ---- e2e: the same kind of steps through the C ABI with host buffers, copies overlapped ---
+    n_e2e = min(steps, e2e_steps or steps)
+    r.clear()
+    host_in = host_hist = host_img = None
+    if rank == 0:
+        host_in = pinned(cells, "uint32")
+        host_hist = pinned(cells, "uint32").reshape((n_ch, h, w) if channels else (h, w))
+        host_img = pinned(cells, "uint16")
+    ranges = [step_range(k, rank, world, per_gpu, first=1 << 57) for k in range(n_e2e)]
+    cx.barrier()
+    e2e_s = e2e_pipeline(r, ranges, host_in, host_hist, host_img, n_ch, (h, w), rank, world,
+                         hist_t, dist)
+    cx.barrier()
+    (e2e_s,) = cx.allmax(e2e_s)
+    e2e_value = per_gpu * n_e2e * world / e2e_s
 
     if rank != 0:
         r.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline: FP64-pipe issue rate; peak = in-run DFMA probe ------------
-    S = samples_total
-    t_s = dev_ms * 1e-3  # render kernels only (max over ranks not needed: rank 0's own share)
-    S0 = per_gpu * args.steps
-    scale = 1.0 / world  # counters were summed over ranks; roofline is per GPU
-    lane_exec = (14 * S0 + 8 * cnt["executed_iters"] * scale + 8 * cnt["orbit_points"] * scale)
-    lane_ref = (14 * S0 + 8 * cnt["escape_iters"] * scale + 8 * cnt["orbit_points"] * scale)
-    roofline = {
-        "bound": "fp64-pipe", "unit": "Tlane-instr/s",
-        "achieved": lane_exec / t_s / 1e12, "peak": fp64_peak / 1e12,
-        "frac": lane_exec / t_s / fp64_peak,
-        "traffic": NCU_DRAM_BYTES_PER_2P30_LAUNCH.get(args.workload),
-        "traffic_note": "DRAM bytes (read+write) of one render_persistent_kernel launch over 2^30 "
-                        "samples of this workload, ncu --set full (profiles/r01_summary.md); the "
-                        "kernel is FP64/issue bound, its algorithmic memory traffic is 4 B per "
-                        "in-canvas increment at L2",
-        "peak_source": "in-run independent-DFMA probe (buddha_probe_fp64_peak); MEASURED_PEAKS.json "
-                       "has no FP64 figure",
-        "numerator": "reference-dataflow FP64 instructions (14*S + 8*E + 8*P, SURVEY.md 8(d)) with "
-                     "E = iterations actually executed",
-        "achieved_reference_work": lane_ref / t_s / 1e12,
-        "frac_reference_work": lane_ref / t_s / fp64_peak,
-        "note": "reference_work counts the iterations the reference must run for the same output "
-                "(E includes max-iter for never-escaping samples); the exact periodicity shortcut "
-                "and the 4-instruction scaled step make it exceed 1",
-    }
-
-    line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "%s: %dx%d canvas %s, max-iter %d, min-cutoff %d" %
-                   (args.workload, w, h, list(canvas), m, c),
-                   "samples_per_step_per_gpu": per_gpu, "seed": 1337,
-                   "l2": "256 MiB flush write between timed steps",
-                   "parallelism": "%d x disjoint Philox ranges%s" %
-                   (world, " + 1 ncclReduce(sum) at the end (timed)" if world > 1 else ""),
-                   "shortcut": not args.no_shortcut,
-                   **({"channels": channels, "fused": "one pass feeds all channels"}
-                      if channels else {})},
+        return None
+    scale = 1.0 / world  # counters were summed over ranks; the rooflines are per GPU
+    t_s = dev_ms * 1e-3
+    S0 = per_gpu * steps
+    res = {
+        "workload": name, "value": value, "samples_per_s": value, "unit": "samples/s",
+        "steps": steps, "samples_per_step_per_gpu": per_gpu, "ms_per_step": total_ms / steps,
         "orbit_points_per_s": cnt["orbit_points"] / (total_ms * 1e-3),
-        "increments_per_s": increments_total / (total_ms * 1e-3),
-        "wall_ms_per_step": wall_ms / args.steps, "merge_ms": merge_ms,
+        "increments_per_s": inc_total / (total_ms * 1e-3),
+        "wall_ms_per_step": wall_ms / steps, "merge_ms": merge_max,
         "counters": {k: cnt[k] for k in ("rejected", "hit_max", "too_early", "accepted",
                                          "escape_iters", "executed_iters", "orbit_points",
                                          "increments", "shortcut_hits", "exact_bins")},
-        "e2e": {"value": e2e_value, "unit": "samples/s",
+        "gpu_launches": cnt["kernel_launches"] // world,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "steps": n_e2e,
                 "h2d_bytes_per_step": cells * 4, "d2h_bytes_per_step": cells * 4 + cells * 2,
-                "what": "per step: load_histogram (H2D) + render_samples + read_histogram (D2H) + "
-                        "tonemap_u16 (D2H), pinned host buffers, wall clock"},
-        "gpu_launches": cnt["kernel_launches"] // world if world > 1 else cnt["kernel_launches"],
-        "clocks": clocks, "roofline": roofline,
+                "frac_of_device_rate": e2e_value / value,
+                "what": "per step through the C ABI, pinned host buffers, wall clock: "
+                        "add_histogram_async (H2D) + render_samples_async%s + snapshot + "
+                        "read_snapshot (D2H) + tonemap_snapshot_u16 (D2H); the copies of step k-1 "
+                        "overlap the render of step k" %
+                        (" + ncclReduce to rank 0 (only rank 0 copies)" if world > 1 else "")},
+        "clocks": clocks,
+        "roofline": make_roofline(S0, cnt, scale, t_s, fp64_peak,
+                                  clocks["sm_mhz"] if clocks else None, name),
     }
+    res["roofline_red"] = make_red_roofline(r, cnt, scale, t_s, hist_bytes, tiled, name)
+    if channels:
+        res["channels"] = channels
+    r.close()
+    if baselines and world == 1:
+        wl = WORKLOADS[name]
+        refs = [run_reference_binary((w, h, mk, ck, canvas, 0), 3.0)
+                for (mk, ck) in (channels or [(m, c)])]
+        if all(refs):
+            res["reference_cuda"] = {"value": 1.0 / sum(1.0 / x[0] for x in refs),
+                                     "unit": "samples/s", "passes": [x[1] for x in refs],
+                                     "seconds": [x[2] for x in refs],
+                                     "what": "unmodified cudabrot.cu built for sm_100a, same "
+                                             "workload, this GPU, -t 3 (one run per channel)"}
+            res["vs_reference_cuda"] = res["value"] / res["reference_cuda"]["value"]
+    return res
 
-    # second roofline: red.global.add.u32 rate vs a probe scattering over the same footprint
-    red_peak = r.probe_red_peak(hist_t.numel() * 4)
-    line["roofline_red"] = {
-        "bound": "l2-red", "unit": "Gred/s", "achieved": cnt["increments"] * scale / t_s / 1e9,
-        "peak": red_peak / 1e9, "frac": cnt["increments"] * scale / t_s / red_peak,
-        "footprint_bytes": hist_t.numel() * 4,
-        "peak_source": "in-run probe: red.global.add.u32 to uniformly random cells of an array of "
-                       "the histogram's size (buddha_probe_red_peak)",
-        "algorithmic_bytes_per_increment": 4}
+
+def run_strong(cx, name="cfg3_m20000", n_total=1 << 38):
+    """Strong scaling on the render north_star names for 8 GPUs: a FIXED range of n_total sample
+    indices split contiguously over the ranks, one ncclReduce(sum) of the 1.6 GB histograms timed
+    inside the job, and the digest of the merged histogram -- which must be the same for every
+    number of GPUs (histogram(N GPUs) == histogram(1 GPU))."""
+    import cudabrot_b200 as B
+    from cudabrot_b200.sharding import contiguous_split
+    torch, dist = cx.torch, cx.dist
+    rank, world = cx.rank, cx.world
+    w, h, m, c, canvas, _ = WORKLOADS[name]
+    r = B.Renderer(w, h, m, c, canvas=canvas, seed=1337, device=cx.local_rank)
+    hist_t = r.histogram_as_tensor()
+    r.render_samples(1 << 56, 1 << 26)      # warm-up: sizes the tile lists, loads the kernels
+    if world > 1:
+        dist.reduce(hist_t, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+    r.clear()
+    r.reset_counters()
+    sampler = ClockSampler(cx.local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    f, n = contiguous_split(0, n_total, rank, world)
+    cx.barrier()
+    sampler.mark_start()
+    wall0 = time.perf_counter()
+    r.render_samples(f, n)
+    render_ms = r.last_render_ms()
+    merge_ms = 0.0
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.reduce(hist_t, dst=0, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize()
+        merge_ms = e0.elapsed_time(e1)       # includes waiting for the slowest rank's render
+    cx.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms, render_max, wall_ms = cx.allmax(render_ms + merge_ms, render_ms, wall_ms)
+    cnt, _ = cx.allsum_counters(r.counters())
+    res = None
+    if rank == 0:
+        res = {"workload": name, "n_total": n_total, "split": "contiguous, rank r of N",
+               "ms": total_ms, "render_ms_max": render_max, "merge_ms": merge_ms,
+               "wall_ms": wall_ms, "samples_per_s": n_total / (total_ms * 1e-3),
+               "orbit_points_per_s": cnt["orbit_points"] / (total_ms * 1e-3),
+               "hist_fnv": "%016x" % r.digest(0),
+               "hist_fnv_what": "buddha_histogram_digest of the merged histogram on rank 0 "
+                                "(blocked FNV-1a-64, include/buddha.h)",
+               "merge_bytes": hist_t.numel() * 4,
+               "counters": {k: cnt[k] for k in ("accepted", "orbit_points", "increments",
+                                                "executed_iters")},
+               "clocks": clocks, "timing": "render: CUDA events on the library's stream; merge: "
+               "CUDA events around ncclReduce; ms = max over ranks of their sum"}
+    r.close()
+    return res
+
+
+def cli_merge_check(cx):
+    """buddha_merge (the in-process ncclReduce behind `cudabrot --gpus N`): the PGM written with
+    --gpus N must equal the one written with --gpus 1 for the same sample range."""
+    import hashlib
+    from cudabrot_b200 import capi
+    if cx.rank != 0:
+        return None
+    out = {"gpus": cx.world}
+    with tempfile.TemporaryDirectory() as tmp:
+        shas = []
+        for g in sorted({cx.world, 1}, reverse=True):
+            pgm = os.path.join(tmp, "g%d.pgm" % g)
+            cmd = [capi.CLI_PATH, "--gpus", str(g), "-w", "2000", "-h", "2000", "-m", "2000", "-c",
+                   "20", "--samples", str(1 << 30), "-o", pgm]
+            try:
+                p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            except (OSError, subprocess.TimeoutExpired) as e:
+                out["error"] = str(e)
+                return out
+            if p.returncode != 0 or not os.path.exists(pgm):
+                out["error"] = (p.stdout + p.stderr)[-300:]
+                return out
+            shas.append(hashlib.sha256(open(pgm, "rb").read()).hexdigest()[:16])
+        out["pgm_sha_gpusN"], out["pgm_sha_gpus1"] = shas[0], shas[-1]
+        out["equal"] = shas[0] == shas[-1]
+        out["what"] = "bin/cudabrot --gpus N vs --gpus 1, 2000x2000 -m 2000 -c 20 --samples 2^30"
+    return out
+
+
+def native_arm(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tmp = torch.zeros(1024, dtype=torch.int32, device="cuda")
+        dist.reduce(tmp, dst=0, op=dist.ReduceOp.SUM)   # initialises NCCL outside any timed region
+        torch.cuda.synchronize()
+    cx = Ctx(args, rank, world, local_rank)
+    w, h, m, c, canvas, default_step = wl
+    per_gpu = args.samples_per_step or default_step
+
+    head = run_workload(cx, args.workload, args.steps, args.warmup, per_gpu)
+    extras, strong, cli = [], None, None
+    if not args.no_extras:
+        strong = run_strong(cx, n_total=args.strong_samples)
+        cx.barrier()
+        cli = cli_merge_check(cx)
+        cx.barrier()
+        for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
+            if name == args.workload:
+                continue
+            res = run_workload(cx, name, 0, 1, WORKLOADS[name][5], min_seconds=1.3, e2e_steps=6,
+                               baselines=not args.skip_baselines)
+            if res:
+                extras.append(res)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": make_config(args.workload, wl),
+        "run": {"samples_per_step_per_gpu": per_gpu,
+                "parallelism": "%d x disjoint Philox ranges%s" %
+                (world, " + 1 ncclReduce(sum) at the end (timed)" if world > 1 else ""),
+                "shortcut": not args.no_shortcut},
+        "orbit_points_per_s": head["orbit_points_per_s"],
+        "increments_per_s": head["increments_per_s"],
+        "wall_ms_per_step": head["wall_ms_per_step"], "merge_ms": head["merge_ms"],
+        "counters": head["counters"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+        "clocks": head["clocks"], "roofline": head["roofline"], "roofline_red": head["roofline_red"],
+    }
+    line["e2e"]["merge_ms"] = head["merge_ms"]
+    # the driver keeps `roofline`, `e2e`, `config`, `clocks`, `cpu_baseline` whole: the other
+    # BASELINE workloads and the strong-scaling job ride inside `roofline` as well as at top level
+    if strong:
+        line["strong_cfg3_m20000"] = strong
+        line["roofline"]["strong_cfg3_m20000"] = strong
+    if cli:
+        line["cli_merge"] = cli
+        line["roofline"]["cli_merge"] = cli
+    if extras:
+        line["workloads"] = extras
+        line["roofline"]["workloads"] = extras
     if world == 1 and not args.skip_baselines:
-        r.close()
+        channels = CHANNELS.get(args.workload)
         line["cpu_baseline"] = time_cpu_oracle(wl, channels=channels)
         refs = [run_reference_binary((w, h, mk, ck, canvas, 0), 5.0)
                 for (mk, ck) in (channels or [(m, c)])]
@@ -445,11 +718,7 @@ def native_arm(args, wl, rank, world, local_rank):
                                       "seconds": [x[2] for x in refs],
                                       "what": "unmodified cudabrot.cu built for sm_100a, same "
                                               "workload, this GPU, -t 5 (one run per channel)"}
-    else:
-        r.close()
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
@@ -463,6 +732,9 @@ def main():
     ap.add_argument("--samples-per-step", type=int, default=0)
     ap.add_argument("--no-shortcut", action="store_true")
     ap.add_argument("--skip-baselines", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the headline workload: no strong-scaling job, no other workloads")
+    ap.add_argument("--strong-samples", type=int, default=1 << 38)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

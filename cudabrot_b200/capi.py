@@ -31,6 +31,8 @@ EXPORTS = [
     "buddha_device_histogram", "buddha_stream", "buddha_merge", "buddha_probe_fp64_peak",
     "buddha_probe_red_peak", "buddha_read_channel", "buddha_tonemap_channel_u16",
     "buddha_get_channel_counters", "buddha_device_histogram_cells",
+    "buddha_add_histogram_async", "buddha_snapshot", "buddha_read_snapshot",
+    "buddha_tonemap_snapshot_u16", "buddha_histogram_digest",
 ]
 MAX_CHANNELS = 4
 
@@ -128,6 +130,12 @@ def lib():
     L.buddha_merge.argtypes = [C.POINTER(ctx), C.c_int, C.c_int]
     L.buddha_probe_fp64_peak.argtypes = [ctx, dblp]
     L.buddha_probe_red_peak.argtypes = [ctx, C.c_size_t, dblp]
+    L.buddha_add_histogram_async.argtypes = [ctx, C.c_void_p, C.c_size_t]
+    L.buddha_snapshot.argtypes = [ctx]
+    L.buddha_read_snapshot.argtypes = [ctx, C.c_void_p, C.c_size_t]
+    L.buddha_tonemap_snapshot_u16.argtypes = [ctx, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                                              C.c_size_t, u32p, dblp]
+    L.buddha_histogram_digest.argtypes = [ctx, C.c_int, u64p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("buddha_abi_version",):

@@ -59,7 +59,6 @@ struct buddha_ctx {
   uint32_t *d_hist;
   unsigned long long *d_cursor;   // offset handed out so far in the current launch
   unsigned long long *d_counters; // kCntSlots accumulators
-  uint32_t *d_max;
   OrbitSpill spill[2];            // grid-wide lists of orbits left over by the render kernel
   unsigned int *d_spill_next[2];  // (two: the drain of launch k overlaps the render of launch k+1)
   // tile-binned scatter (histograms far beyond L2), see scatter() in buddha_kernels.cuh
@@ -76,11 +75,24 @@ struct buddha_ctx {
   uint32_t *d_tbase;              // per tile: first pool entry (inside one pool half)
   size_t pool_entries;
   double tile_pts_per_sample;
-  uint16_t *d_gray;               // tone-mapped image, allocated on first use
-  uint32_t *d_chan;               // fused contexts: one assembled channel, allocated on first use
-  uint16_t *d_lut;
-  uint32_t *d_thr;
-  uint32_t lut_capacity;
+  // tone-map scratch: [0] for the live histogram (render stream), [1] for the snapshot (copy stream)
+  struct ToneBufs {
+    uint32_t *d_max;
+    uint16_t *d_gray;             // tone-mapped image, allocated on first use
+    uint32_t *d_chan;             // fused contexts: one assembled channel, allocated on first use
+    uint16_t *d_lut;
+    uint32_t *d_thr;
+    uint32_t lut_capacity;
+  } tone[2];
+  // asynchronous host transfers (buddha_add_histogram_async, buddha_snapshot, ...)
+  cudaStream_t h2d_stream, d2h_stream;
+  cudaEvent_t ev_staged, ev_added, ev_snap;
+  uint32_t *d_stage;              // counts on their way into the histogram
+  uint32_t *d_snap;               // snapshot of the device histogram (all bands)
+  uint32_t *d_snap_preload;       // fused: snapshot of the loaded counts
+  bool snap_valid;
+  unsigned long long *d_digest;   // block digests (buddha_histogram_digest)
+  size_t digest_capacity;
   RenderParams rp;
   uint64_t candidates;            // host tally: every index in a rendered range is a candidate
   uint64_t launches;
@@ -407,15 +419,13 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaMalloc(&c->d_cursor, sizeof(unsigned long long)));
   CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kTotalCnt));
   CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kTotalCnt, c->stream));
-  CUC(cudaMalloc(&c->d_max, sizeof(uint32_t)));
   for (int b = 0; b < 2; b++) {
-    c->spill[b].capacity = (unsigned)c->grid * kWarpsPerCta * kStackCap;  // every warp spills < kStackCap
+    c->spill[b].capacity = (unsigned)c->grid * kWarpsPerCta * kSpillPerWarp;
     CUC(cudaMalloc(&c->spill[b].entries, sizeof(double4) * c->spill[b].capacity));
     CUC(cudaMalloc(&c->spill[b].steps, sizeof(int) * c->spill[b].capacity));
     CUC(cudaMalloc(&c->spill[b].count, sizeof(unsigned int) * 2));
     c->d_spill_next[b] = c->spill[b].count + 1;
   }
-  CUC(cudaMalloc(&c->d_thr, sizeof(uint32_t) * 65536));
   {
     // tile-binned scatter: on for histograms >= 640 MB (config 3: 1.6 GB; crossover measured with tools/gpu_threshold.py), or when forced (tests)
     const char *e;
@@ -481,7 +491,7 @@ void buddha_destroy(buddha_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->params.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters); cudaFree(c->d_max);
+  cudaFree(c->d_hist); cudaFree(c->d_cursor); cudaFree(c->d_counters);
   for (int b = 0; b < 2; b++) {
     cudaFree(c->spill[b].entries); cudaFree(c->spill[b].steps); cudaFree(c->spill[b].count);
   }
@@ -490,7 +500,16 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
   if (c->ev_applied[1]) cudaEventDestroy(c->ev_applied[1]);
   cudaFree(c->d_pool); cudaFree(c->d_tcount); cudaFree(c->d_tcap); cudaFree(c->d_tbase);
-  cudaFree(c->d_gray); cudaFree(c->d_lut); cudaFree(c->d_thr); cudaFree(c->d_chan);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(c->tone[k].d_max); cudaFree(c->tone[k].d_gray); cudaFree(c->tone[k].d_lut);
+    cudaFree(c->tone[k].d_thr); cudaFree(c->tone[k].d_chan);
+  }
+  if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
+  if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+  if (c->ev_staged) cudaEventDestroy(c->ev_staged);
+  if (c->ev_added) cudaEventDestroy(c->ev_added);
+  if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+  cudaFree(c->d_stage); cudaFree(c->d_snap); cudaFree(c->d_snap_preload); cudaFree(c->d_digest);
   cudaFree(c->d_preload);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -512,21 +531,29 @@ int buddha_clear_histogram(buddha_ctx *c) {
 
 // Fused contexts keep one histogram per BAND on the device (RenderParams); the host API is
 // channel-major: a channel is assembled (sum of its bands + what was loaded) into one buffer.
-static int channel_buffer(buddha_ctx *c) {
-  if (!c->d_chan) CU(c, cudaMalloc(&c->d_chan, sizeof(uint32_t) * c->ch_cells));
-  return BUDDHA_OK;
+// `slot` 0 = the live histogram on the render stream, 1 = the snapshot on the copy stream.
+static const uint32_t *hist_of(buddha_ctx *c, int slot) { return slot ? c->d_snap : c->d_hist; }
+static const uint32_t *preload_of(buddha_ctx *c, int slot) {
+  return slot ? c->d_snap_preload : c->d_preload;
 }
+static cudaStream_t stream_of(buddha_ctx *c, int slot) { return slot ? c->d2h_stream : c->stream; }
 
-static int assemble_channel(buddha_ctx *c, int channel) {
-  int rc = channel_buffer(c);
-  if (rc) return rc;
+// What the host reads as channel `channel`: the histogram itself, or for a fused context the
+// channel assembled into the slot's scratch buffer.
+static int channel_source(buddha_ctx *c, int slot, int channel, const uint32_t **src) {
+  *src = hist_of(c, slot);
+  if (c->n_ch < 2) return BUDDHA_OK;
+  buddha_ctx::ToneBufs &tb = c->tone[slot];
+  if (!tb.d_chan) CU(c, cudaMalloc(&tb.d_chan, sizeof(uint32_t) * c->ch_cells));
   unsigned bands = 0;
   for (int b = 0; b < c->n_bands; b++)
     if ((c->band_set[b] >> channel) & 1u) bands |= 1u << b;
-  channel_sum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
-      c->d_hist, c->d_preload ? c->d_preload + (size_t)channel * c->ch_cells : nullptr, c->d_chan,
+  const uint32_t *pre = preload_of(c, slot);
+  channel_sum_kernel<<<c->sm_count * 8, 256, 0, stream_of(c, slot)>>>(
+      hist_of(c, slot), pre ? pre + (size_t)channel * c->ch_cells : nullptr, tb.d_chan,
       c->ch_cells, bands);
   CU(c, cudaGetLastError());
+  *src = tb.d_chan;
   return BUDDHA_OK;
 }
 
@@ -549,21 +576,23 @@ int buddha_load_histogram(buddha_ctx *c, const uint32_t *host, size_t cells) {
   return BUDDHA_OK;
 }
 
-int buddha_read_channel(buddha_ctx *c, int channel, uint32_t *host, size_t cells) {
+static int read_channel_impl(buddha_ctx *c, int slot, int channel, uint32_t *host, size_t cells) {
   if (!c || !host) return BUDDHA_EINVAL;
   if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
   if (cells != c->ch_cells)
     return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, a channel has %zu", cells, c->ch_cells);
   CU(c, cudaSetDevice(c->params.device));
-  const uint32_t *src = c->d_hist;
-  if (c->n_ch > 1) {
-    int rc = assemble_channel(c, channel);
-    if (rc) return rc;
-    src = c->d_chan;
-  }
-  CU(c, cudaMemcpyAsync(host, src, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  const uint32_t *src = nullptr;
+  int rc = channel_source(c, slot, channel, &src);
+  if (rc) return rc;
+  cudaStream_t st = stream_of(c, slot);
+  CU(c, cudaMemcpyAsync(host, src, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
   return BUDDHA_OK;
+}
+
+int buddha_read_channel(buddha_ctx *c, int channel, uint32_t *host, size_t cells) {
+  return read_channel_impl(c, 0, channel, host, cells);
 }
 
 int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
@@ -695,7 +724,11 @@ static int calibrate_tiles(buddha_ctx *c, uint64_t first, uint64_t count) {
 
 static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   if (count == 0) return BUDDHA_OK;
-  if (first + count < first) return fail(c, BUDDHA_EINVAL, "sample range wraps around 2^64");
+  // the device cursor overshoots the end of a range by up to one chunk per warp of the grid
+  const uint64_t slack = (uint64_t)c->grid * kWarpsPerCta * kMaxChunk;
+  if (first + count < first || first + count > ~(uint64_t)0 - slack)
+    return fail(c, BUDDHA_EINVAL, "sample range must end below 2^64 - %llu",
+                (unsigned long long)slack);
   if (!c->tiled) return launch_render(c, first, count);
   if (!c->tile_calibrated) {
     uint64_t n0 = std::min<uint64_t>(count, (uint64_t)1 << 22);
@@ -754,6 +787,8 @@ int buddha_render_samples(buddha_ctx *c, uint64_t first, uint64_t count) {
 int buddha_render_seconds(buddha_ctx *c, double seconds, volatile int *stop, uint64_t first,
                           uint64_t *samples_done, uint64_t *passes) {
   if (!c) return BUDDHA_EINVAL;
+  if (seconds < 0 && !stop)
+    return fail(c, BUDDHA_EINVAL, "an endless run (seconds < 0) needs a stop flag");
   CU(c, cudaSetDevice(c->params.device));
   uint64_t done = 0, npass = 0;
   // first pass = one reference pass (512*512*50 candidates, cudabrot.cu:20,23,34); later passes
@@ -873,37 +908,38 @@ int buddha_tonemap_u16(buddha_ctx *c, double gamma, int big_endian, uint16_t *ho
   return buddha_tonemap_channel_u16(c, 0, gamma, big_endian, host_out, cells, max_out, scale_out);
 }
 
-int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big_endian,
-                               uint16_t *host_out, size_t cells, uint32_t *max_out,
-                               double *scale_out) {
+static int tonemap_impl(buddha_ctx *c, int slot, int channel, double gamma, int big_endian,
+                        uint16_t *host_out, size_t cells, uint32_t *max_out, double *scale_out) {
   if (!c) return BUDDHA_EINVAL;
   if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
   if (host_out && cells != c->ch_cells)
     return fail(c, BUDDHA_ESIZE, "image buffer has %zu cells, canvas has %zu", cells, c->ch_cells);
-  const uint32_t *d_src = c->d_hist;
-  if (c->n_ch > 1) {
-    int rc = assemble_channel(c, channel);
-    if (rc) return rc;
-    d_src = c->d_chan;
-  }
-  CU(c, cudaSetDevice(c->params.device));
+  CU(c, cudaSetDevice(c->params.device));  // before anything allocates or launches
+  buddha_ctx::ToneBufs &tb = c->tone[slot];
+  cudaStream_t st = stream_of(c, slot);
+  const uint32_t *d_src = nullptr;
+  int rc = channel_source(c, slot, channel, &d_src);
+  if (rc) return rc;
+  if (!tb.d_max) CU(c, cudaMalloc(&tb.d_max, sizeof(uint32_t)));
   const int blocks = c->sm_count * 8;
 
   // pass 1: GetLinearColorScale's maximum (cudabrot.cu:430-435)
-  CU(c, cudaEventRecord(c->ev_ta, c->stream));
-  CU(c, cudaMemsetAsync(c->d_max, 0, sizeof(uint32_t), c->stream));
-  hist_max_kernel<<<blocks, 256, 0, c->stream>>>(d_src, c->ch_cells, c->d_max);
+  if (slot == 0) CU(c, cudaEventRecord(c->ev_ta, st));
+  CU(c, cudaMemsetAsync(tb.d_max, 0, sizeof(uint32_t), st));
+  hist_max_kernel<<<blocks, 256, 0, st>>>(d_src, c->ch_cells, tb.d_max);
   CU(c, cudaGetLastError());
   c->launches += 1;
   uint32_t mx = 0;
-  CU(c, cudaMemcpyAsync(&mx, c->d_max, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemcpyAsync(&mx, tb.d_max, sizeof(mx), cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
   double scale = ((double)0xffff) / ((double)mx);  // :436 (inf when the histogram is empty)
   if (max_out) *max_out = mx;
   if (scale_out) *scale_out = scale;
   if (!host_out) {
-    CU(c, cudaEventRecord(c->ev_tb, c->stream));
-    c->tonemap_timed = true;
+    if (slot == 0) {
+      CU(c, cudaEventRecord(c->ev_tb, st));
+      c->tonemap_timed = true;
+    }
     return BUDDHA_OK;
   }
 
@@ -915,20 +951,22 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
     uint16_t v = tone_value((uint32_t)k, scale, gamma);
     lut[k] = big_endian ? bswap16(v) : v;
   }
-  if (lut_size > c->lut_capacity) {
-    cudaFree(c->d_lut);
-    c->d_lut = nullptr;
-    c->lut_capacity = 0;
-    CU(c, cudaMalloc(&c->d_lut, sizeof(uint16_t) * (size_t)lut_size));
-    c->lut_capacity = lut_size;
+  if (lut_size > tb.lut_capacity) {
+    cudaFree(tb.d_lut);
+    tb.d_lut = nullptr;
+    tb.lut_capacity = 0;
+    CU(c, cudaMalloc(&tb.d_lut, sizeof(uint16_t) * (size_t)lut_size));
+    tb.lut_capacity = lut_size;
   }
-  CU(c, cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * (size_t)lut_size,
-                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(tb.d_lut, lut.data(), sizeof(uint16_t) * (size_t)lut_size,
+                        cudaMemcpyHostToDevice, st));
+  if (!tb.d_thr) CU(c, cudaMalloc(&tb.d_thr, sizeof(uint32_t) * 65536));
+  std::vector<uint32_t> thr;
   if (mx >= lut_size) {
     // counts past the table: thr[v] = smallest count in [0, mx] whose value is >= v (mx + 1 if
     // no count reaches v), on the (monotone) reference expression.  A closed-form inverse gives
     // a guess that a short walk makes exact; bisection if the walk does not settle.
-    std::vector<uint32_t> thr(65536);
+    thr.resize(65536);
     const double top = 0xffff;
 #pragma omp parallel for schedule(static)
     for (int v = 0; v < 65536; v++) {
@@ -949,21 +987,139 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
       thr[v] = (uint32_t)std::min<uint64_t>(cnt, 0xffffffffull);
     }
     thr[0] = 0;
-    CU(c, cudaMemcpyAsync(c->d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,
-                          c->stream));
+    CU(c, cudaMemcpyAsync(tb.d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,
+                          st));
   }
-  if (!c->d_gray) CU(c, cudaMalloc(&c->d_gray, sizeof(uint16_t) * c->ch_cells));
+  if (!tb.d_gray) CU(c, cudaMalloc(&tb.d_gray, sizeof(uint16_t) * c->ch_cells));
 
   // pass 2: the map itself, 4 B read + 2 B written per pixel
-  tonemap_kernel<<<blocks, 256, 0, c->stream>>>(d_src, c->d_gray, c->ch_cells, c->d_lut, lut_size,
-                                                c->d_thr, big_endian ? 1 : 0);
+  tonemap_kernel<<<blocks, 256, 0, st>>>(d_src, tb.d_gray, c->ch_cells, tb.d_lut, lut_size,
+                                         tb.d_thr, big_endian ? 1 : 0);
   CU(c, cudaGetLastError());
   c->launches += 1;
-  CU(c, cudaEventRecord(c->ev_tb, c->stream));
-  c->tonemap_timed = true;
-  CU(c, cudaMemcpyAsync(host_out, c->d_gray, sizeof(uint16_t) * c->ch_cells, cudaMemcpyDeviceToHost,
-                        c->stream));
+  if (slot == 0) {
+    CU(c, cudaEventRecord(c->ev_tb, st));
+    c->tonemap_timed = true;
+  }
+  CU(c, cudaMemcpyAsync(host_out, tb.d_gray, sizeof(uint16_t) * c->ch_cells, cudaMemcpyDeviceToHost,
+                        st));
+  CU(c, cudaStreamSynchronize(st));  // (lut / thr are host vectors read by the copies above)
+  return BUDDHA_OK;
+}
+
+int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big_endian,
+                               uint16_t *host_out, size_t cells, uint32_t *max_out,
+                               double *scale_out) {
+  return tonemap_impl(c, 0, channel, gamma, big_endian, host_out, cells, max_out, scale_out);
+}
+
+// ---- asynchronous host transfers ------------------------------------------------------------
+
+static int transfer_setup(buddha_ctx *c) {
+  if (c->d2h_stream) return BUDDHA_OK;
+  CU(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  CU(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  CU(c, cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+  CU(c, cudaEventCreateWithFlags(&c->ev_added, cudaEventDisableTiming));
+  CU(c, cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+  return BUDDHA_OK;
+}
+
+int buddha_add_histogram_async(buddha_ctx *c, const uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "histogram has %zu cells, canvas needs %zu", cells, c->cells);
+  CU(c, cudaSetDevice(c->params.device));
+  int rc = transfer_setup(c);
+  if (rc) return rc;
+  if (!c->d_stage) CU(c, cudaMalloc(&c->d_stage, sizeof(uint32_t) * c->cells));
+  uint32_t *dst = c->d_hist;
+  if (c->n_ch > 1) {  // loaded counts stay channel-major beside the bands (buddha_load_histogram)
+    if (!c->d_preload) {
+      CU(c, cudaMalloc(&c->d_preload, sizeof(uint32_t) * c->cells));
+      CU(c, cudaMemsetAsync(c->d_preload, 0, sizeof(uint32_t) * c->cells, c->stream));
+    }
+    dst = c->d_preload;
+  }
+  // the staging buffer is free again once the previous add kernel has run; the copy itself only
+  // waits for that, not for renders enqueued since, so it overlaps them
+  CU(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_added, 0));  // (no-op before the first add)
+  CU(c, cudaMemcpyAsync(c->d_stage, host, sizeof(uint32_t) * cells, cudaMemcpyHostToDevice,
+                        c->h2d_stream));
+  CU(c, cudaEventRecord(c->ev_staged, c->h2d_stream));
+  CU(c, cudaStreamWaitEvent(c->stream, c->ev_staged, 0));
+  add_cells_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dst, c->d_stage, cells);
+  CU(c, cudaGetLastError());
+  CU(c, cudaEventRecord(c->ev_added, c->stream));
+  c->launches += 1;
+  return BUDDHA_OK;
+}
+
+int buddha_snapshot(buddha_ctx *c) {
+  if (!c) return BUDDHA_EINVAL;
+  CU(c, cudaSetDevice(c->params.device));
+  int rc = transfer_setup(c);
+  if (rc) return rc;
+  if (!c->d_snap) CU(c, cudaMalloc(&c->d_snap, sizeof(uint32_t) * c->dev_cells));
+  CU(c, cudaMemcpyAsync(c->d_snap, c->d_hist, sizeof(uint32_t) * c->dev_cells,
+                        cudaMemcpyDeviceToDevice, c->stream));
+  if (c->d_preload) {
+    if (!c->d_snap_preload) CU(c, cudaMalloc(&c->d_snap_preload, sizeof(uint32_t) * c->cells));
+    CU(c, cudaMemcpyAsync(c->d_snap_preload, c->d_preload, sizeof(uint32_t) * c->cells,
+                          cudaMemcpyDeviceToDevice, c->stream));
+  }
+  CU(c, cudaEventRecord(c->ev_snap, c->stream));
+  CU(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_snap, 0));
+  c->snap_valid = true;
+  return BUDDHA_OK;
+}
+
+int buddha_read_snapshot(buddha_ctx *c, uint32_t *host, size_t cells) {
+  if (!c || !host) return BUDDHA_EINVAL;
+  if (!c->snap_valid) return fail(c, BUDDHA_EINVAL, "no snapshot has been taken");
+  if (cells != c->cells)
+    return fail(c, BUDDHA_ESIZE, "buffer has %zu cells, canvas has %zu", cells, c->cells);
+  for (int k = 0; k < c->n_ch; k++) {
+    int rc = read_channel_impl(c, 1, k, host + (size_t)k * c->ch_cells, c->ch_cells);
+    if (rc) return rc;
+  }
+  return BUDDHA_OK;
+}
+
+int buddha_tonemap_snapshot_u16(buddha_ctx *c, int channel, double gamma, int big_endian,
+                                uint16_t *host_out, size_t cells, uint32_t *max_out,
+                                double *scale_out) {
+  if (!c) return BUDDHA_EINVAL;
+  if (!c->snap_valid) return fail(c, BUDDHA_EINVAL, "no snapshot has been taken");
+  return tonemap_impl(c, 1, channel, gamma, big_endian, host_out, cells, max_out, scale_out);
+}
+
+int buddha_histogram_digest(buddha_ctx *c, int channel, uint64_t *digest) {
+  if (!c || !digest) return BUDDHA_EINVAL;
+  if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
+  CU(c, cudaSetDevice(c->params.device));
+  const uint32_t *src = nullptr;
+  int rc = channel_source(c, 0, channel, &src);
+  if (rc) return rc;
+  const size_t n_blocks = (c->ch_cells + kDigestBlock - 1) / kDigestBlock;
+  if (n_blocks > c->digest_capacity) {
+    cudaFree(c->d_digest);
+    c->d_digest = nullptr;
+    c->digest_capacity = 0;
+    CU(c, cudaMalloc(&c->d_digest, sizeof(unsigned long long) * n_blocks));
+    c->digest_capacity = n_blocks;
+  }
+  digest_blocks_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(src, c->ch_cells, c->d_digest,
+                                                                n_blocks);
+  CU(c, cudaGetLastError());
+  c->launches += 1;
+  std::vector<unsigned long long> blocks(n_blocks);
+  CU(c, cudaMemcpyAsync(blocks.data(), c->d_digest, sizeof(unsigned long long) * n_blocks,
+                        cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  unsigned long long h = kFnvBasis;
+  for (size_t b = 0; b < n_blocks; b++) h = (h ^ blocks[b]) * kFnvPrime;
+  *digest = h;
   return BUDDHA_OK;
 }
 
@@ -984,18 +1140,52 @@ int buddha_merge(buddha_ctx **ctxs, int n, int root) {
   if (!ctxs || n < 1 || root < 0 || root >= n) return BUDDHA_EINVAL;
   if (n == 1) return BUDDHA_OK;
   buddha_ctx *r = ctxs[root];
+  if (!r) return BUDDHA_EINVAL;
+  bool any_preload = false;
   for (int i = 0; i < n; i++) {
-    if (!ctxs[i]) return BUDDHA_EINVAL;
-    if (ctxs[i]->dev_cells != r->dev_cells) return fail(r, BUDDHA_ESIZE, "contexts differ in canvas size");
+    const buddha_ctx *x = ctxs[i];
+    if (!x) return BUDDHA_EINVAL;
+    // the cells only add up if every context bins the same canvas into the same bands
+    const buddha_params &a = x->params, &b = r->params;
+    bool same = a.width == b.width && a.height == b.height && a.min_real == b.min_real &&
+                a.max_real == b.max_real && a.min_imag == b.min_imag && a.max_imag == b.max_imag &&
+                x->n_ch == r->n_ch && x->n_bands == r->n_bands && x->dev_cells == r->dev_cells &&
+                x->rp.n_seg == r->rp.n_seg;
+    for (int k = 0; same && k < x->n_bands; k++) same = x->band_set[k] == r->band_set[k];
+    for (int k = 0; same && k < x->rp.n_seg; k++)
+      same = x->rp.seg_start[k] == r->rp.seg_start[k] && x->rp.seg_band[k] == r->rp.seg_band[k];
+    if (!same) return fail(r, BUDDHA_ESIZE, "context %d differs from the root in canvas or channels", i);
+    for (int j = 0; j < i; j++)
+      if (ctxs[j]->params.device == x->params.device)
+        return fail(r, BUDDHA_EINVAL, "contexts %d and %d share device %d", j, i, x->params.device);
+    any_preload = any_preload || x->d_preload != nullptr;
+  }
+  int prev_dev = 0;
+  CU(r, cudaGetDevice(&prev_dev));
+  // fused contexts keep loaded counts channel-major beside the bands: they are summed as well
+  if (any_preload) {
+    for (int i = 0; i < n; i++) {
+      buddha_ctx *x = ctxs[i];
+      if (x->d_preload) continue;
+      CU(x, cudaSetDevice(x->params.device));
+      CU(x, cudaMalloc(&x->d_preload, sizeof(uint32_t) * x->cells));
+      CU(x, cudaMemsetAsync(x->d_preload, 0, sizeof(uint32_t) * x->cells, x->stream));
+    }
   }
   NcclApi *nccl = load_nccl();
-  if (!nccl) return fail(r, BUDDHA_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  if (!nccl) {
+    cudaSetDevice(prev_dev);
+    return fail(r, BUDDHA_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  }
   std::vector<int> devs(n);
   std::vector<void *> comms(n, nullptr);
   for (int i = 0; i < n; i++) devs[i] = ctxs[i]->params.device;
   int rc = nccl->CommInitAll(comms.data(), n, devs.data());
-  if (rc) return fail(r, BUDDHA_ENCCL, "ncclCommInitAll: %s",
-                      nccl->GetErrorString ? nccl->GetErrorString(rc) : "error");
+  if (rc) {
+    cudaSetDevice(prev_dev);
+    return fail(r, BUDDHA_ENCCL, "ncclCommInitAll: %s",
+                nccl->GetErrorString ? nccl->GetErrorString(rc) : "error");
+  }
   rc = nccl->GroupStart();
   for (int i = 0; i < n && !rc; i++) {
     cudaSetDevice(devs[i]);
@@ -1004,11 +1194,22 @@ int buddha_merge(buddha_ctx **ctxs, int n, int root) {
   }
   int rc2 = nccl->GroupEnd();
   if (!rc) rc = rc2;
+  if (!rc && any_preload) {
+    rc = nccl->GroupStart();
+    for (int i = 0; i < n && !rc; i++) {
+      cudaSetDevice(devs[i]);
+      rc = nccl->Reduce(ctxs[i]->d_preload, ctxs[i]->d_preload, r->cells, 3, 0, root, comms[i],
+                        ctxs[i]->stream);
+    }
+    rc2 = nccl->GroupEnd();
+    if (!rc) rc = rc2;
+  }
   for (int i = 0; i < n; i++) {
     cudaSetDevice(devs[i]);
     cudaStreamSynchronize(ctxs[i]->stream);
   }
   for (int i = 0; i < n; i++) nccl->CommDestroy(comms[i]);
+  cudaSetDevice(prev_dev);  // the caller's current device is not ours to change
   if (rc) return fail(r, BUDDHA_ENCCL, "ncclReduce: %s",
                       nccl->GetErrorString ? nccl->GetErrorString(rc) : "error");
   return BUDDHA_OK;

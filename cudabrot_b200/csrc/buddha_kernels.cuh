@@ -22,10 +22,29 @@
 
 namespace buddha {
 
-constexpr int kWarpsPerCta = 11;                // 2 CTAs x 11 warps x 10 KB of stacks fill one SM
-constexpr int kCtasPerSm = 2;
+// Occupancy: 3 CTAs x 8 warps per SM (24 warps, <= 80 registers, 8176 B of work stacks per warp).
+// Measured (tools/gpu_ab.sh, profiles/r02_occupancy_ab.txt): 22, 24, 26 and 27 warps per SM are within
+// 2 % of each other -- the kernel is bound by instruction issue, not by latency -- and 3 x 8 leaves
+// the registers the co-resident apply / drain CTAs of the tiled pipeline need.
+// BUDDHA_WARPS_PER_CTA / BUDDHA_CTAS_PER_SM: A/B builds.
+#ifndef BUDDHA_WARPS_PER_CTA
+#define BUDDHA_WARPS_PER_CTA 8
+#endif
+#ifndef BUDDHA_CTAS_PER_SM
+#define BUDDHA_CTAS_PER_SM 3
+#endif
+constexpr int kWarpsPerCta = BUDDHA_WARPS_PER_CTA;
+constexpr int kCtasPerSm = BUDDHA_CTAS_PER_SM;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-constexpr int kStackCap = 64;                  // entries per work stack (5 stacks per warp)
+// Work stacks (entries).  A phase pops at most 32 entries and pushes at most 32, and runs only
+// while its targets hold < 32, so no stack exceeds 63.  `late` and `orb` share one array and grow
+// towards each other, and so do `t1` and `t2`: t1 + t2 <= 63 + 31, and late + orb <= kZJoint + 32
+// because every phase that pushes to them starts only while late + orb <= kZJoint (else `late`
+// runs first, with whatever it holds).
+constexpr int kDeepCap = 63;
+constexpr int kZCap = 87, kZJoint = kZCap - 32;
+constexpr int kCCap = 94;
+constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel with < 32 accepted samples
 constexpr int kChunk = 4096;                   // granularity of launch sizes (host side)
 constexpr int kMinChunk = 1024, kMaxChunk = 16384;  // sample indices a warp takes per cursor grab
 constexpr int kGenSteps = 2;                   // escape-test steps done by the sampler itself
@@ -138,6 +157,7 @@ __device__ __forceinline__ uint4 philox4x32_10(unsigned long long s, const Rende
   uint32_t c0 = (uint32_t)s, c1 = (uint32_t)(s >> 32), c2 = 0u, c3 = 0u;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
+    // (one IMAD.WIDE each; splitting them into IMAD.HI + IMAD was measured 4..6 % slower)
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ p.key0[r];
@@ -167,6 +187,34 @@ __device__ __forceinline__ bool rejected2(double cx, double cy) {
   double t = __dadd_rn(cx, 2.0);            // 2 * (re + 1)
   double b = __fma_rn(t, t, i2);            // 4 * fma(t, t, i2)
   return (lhs < i2) || (b < 0.25);
+}
+
+// Conservative membership test for the period-3 hyperbolic components (the two period-3 bulbs and
+// the cardioid of the period-3 copy at c = -1.7549), SURVEY.md 8(f)3.  On those components the
+// multiplier lambda of the attracting 3-cycle satisfies
+//     c^3 + 2 c^2 + (1 - lambda/8) c + (1 - lambda/8)^2 = 0          (Giarrusso & Fisher 1995),
+// a quadratic in mu = 1 - lambda/8, so  lambda = 8 + 4c -+ 4c sqrt(-7 - 4c), and c lies in a
+// period-3 component iff one of the two roots has |lambda| < 1.  A candidate with
+// |lambda|^2 < kP3Max = 0.96 sits well inside: its critical orbit converges to the cycle at rate
+// 0.98 per period and stays ~1e-3 away from the Julia set, 13 orders of magnitude more than the
+// rounding noise of the FP64 iteration, so the reference's loop runs to max_iterations.  It is
+// `hit max` without being iterated (57 % of the period-3 detection work, which is 42 % of all
+// never-escaping samples).  FP32 is ample: |lambda|^2 is formed to ~1e-5.  Histogram-neutral like
+// the periodicity check; BUDDHA_F_NO_SHORTCUT turns both off and the parity tests run both ways.
+constexpr float kP3Max = 0.96f;
+
+__device__ __forceinline__ bool in_period3_component(double cx2, double cy2) {
+  const float a = 0.5f * (float)cx2, b = 0.5f * (float)cy2;            // c = a + b i
+  const float wr = __fmaf_rn(-4.0f, a, -7.0f), wi = -4.0f * b;          // w = -7 - 4c
+  const float mw = sqrtf(__fmaf_rn(wr, wr, wi * wi));
+  const float sr = sqrtf(fmaxf(0.5f * (mw + wr), 0.0f));               // s = sqrt(w), principal
+  const float si = copysignf(sqrtf(fmaxf(0.5f * (mw - wr), 0.0f)), wi);
+  const float tr = __fmaf_rn(a, sr, -b * si), ti = __fmaf_rn(a, si, b * sr);  // t = c s
+  const float br = __fmaf_rn(4.0f, a, 8.0f), bi = 4.0f * b;             // 8 + 4c
+  const float l1r = __fmaf_rn(-4.0f, tr, br), l1i = __fmaf_rn(-4.0f, ti, bi);
+  const float l2r = __fmaf_rn(4.0f, tr, br), l2i = __fmaf_rn(4.0f, ti, bi);
+  const float m1 = __fmaf_rn(l1r, l1r, l1i * l1i), m2 = __fmaf_rn(l2r, l2r, l2i * l2i);
+  return fminf(m1, m2) < kP3Max;
 }
 
 // ---- scatter --------------------------------------------------------------------------------
@@ -341,27 +389,27 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 // Lanes that have escaped keep stepping until their tier ends; their values grow to inf/NaN,
 // which no later code reads (the `alive` predicate is sticky and NaN compares false).
 
-struct CStack {  // candidates that re-compute their state from c
-  double2 c[kStackCap];
-};
-
-struct ZStack {  // late: it = iterations done; orbit: it = steps still to record
-  double2 c[kStackCap], z[kStackCap];
-  int it[kStackCap];
-};
-
-// `deep` entries carry their Brent checkpoint, so suspending a lane does not restart the
-// periodicity search (long cycles need long uninterrupted windows).
-struct DeepStack {
-  double2 c[kStackCap], z[kStackCap], r[kStackCap];
-  uint2 meta[kStackCap];  // (iterations done, age)
-};
-
+// Shared-memory work stacks of one warp (structure of arrays: 16-byte accesses, no conflicts).
+//   c_*      t1 (slots 0 up) and t2 (slots kCCap-1 down): candidates that re-compute their state from c
+//   z_*      late (0 up): it = iterations done; orb (kZCap-1 down): it = steps still to record
+//   deep_*   carry their checkpoint, so suspending a lane does not restart the periodicity search
+//            (long cycles need long uninterrupted windows); meta = (last, age): the age after which
+//            no further full round fits below max_it, and the rounds spent in deep so far
 struct WarpQueues {
-  DeepStack deep;
-  ZStack late, orb;
-  CStack t1, t2;
+  double2 deep_c[kDeepCap], deep_z[kDeepCap], deep_r[kDeepCap];
+  double2 z_c[kZCap], z_z[kZCap];
+  double2 c_c[kCCap];
+  uint2 deep_meta[kDeepCap];
+  int z_it[kZCap];
+  int pad[(4 - (2 * kDeepCap + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
 };
+static_assert(sizeof(WarpQueues) % 16 == 0, "stack arrays must stay 16-byte aligned");
+
+// slot of entry i of the stack growing up from 0 / down from the top of a shared array
+template <bool kDown, int kCap>
+__device__ __forceinline__ int slot_of(int i) { return kDown ? kCap - 1 - i : i; }
+constexpr bool kLate = false, kOrb = true;  // the two stacks in z_*
+constexpr bool kT1 = false, kT2 = true;     // the two stacks in c_*
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
@@ -373,25 +421,35 @@ struct WarpState {
   uint32_t n_rej, n_hit, n_acc, n_cyc, n_exact;
   uint32_t steps;      // iterations that advanced a sample (count for escape_iters AND executed)
   uint32_t skipped;    // iterations the periodicity shortcut did not have to run (escape_iters only)
-  uint32_t wasted;     // deep rounds that were rolled back (executed only)
+  // deep rounds: a lane subtracts a sample's age when it loads it and adds the age back when the
+  // sample finishes or is suspended, so the sum is the number of rounds run (transiently negative
+  // per lane, hence signed); d_out = rounds rolled back because the sample had escaped in them.
+  // escape_iters += kBlock * (d_rounds - d_out), executed += kBlock * d_rounds.
+  int32_t d_rounds;
+  uint32_t d_out;
   uint32_t p_pts, p_inc;
   uint32_t ch_inc[kMaxBands];     // fused render only: increments per band
 };
 
-// Warp-reduce nine per-lane counters and add them to the global accumulators.  Deliberately not
-// inlined (arguments by value, so the caller's state stays in registers): it runs once per 4096
-// candidates and would otherwise be replicated at every call site.
+// Warp-reduce the per-lane counters and add them to the global accumulators.  Deliberately not
+// inlined (arguments by value, so the caller's state stays in registers): it runs a few times per
+// launch and would otherwise be replicated at every call site.
 __device__ __noinline__ void flush_values(unsigned long long *counters, uint32_t n_rej,
-                                          uint32_t n_hit, uint32_t n_acc, uint32_t e_ref,
-                                          uint32_t e_ref2, uint32_t p_pts, uint32_t p_inc,
-                                          uint32_t e_exec2, uint32_t n_cyc, uint32_t n_exact) {
-  const uint32_t v[kCntSlots] = {n_rej, n_hit, 0u, n_acc, e_ref, p_pts, p_inc, e_ref, n_cyc, n_exact};
+                                          uint32_t n_hit, uint32_t n_acc, uint32_t steps,
+                                          uint32_t skipped, uint32_t p_pts, uint32_t p_inc,
+                                          int32_t d_rounds, uint32_t d_out, uint32_t n_cyc,
+                                          uint32_t n_exact) {
+  // (64-bit two's complement: a transiently negative d_rounds adds up correctly)
+  const long long deep_exec = (long long)d_rounds * kBlock;
+  const long long deep_ref = deep_exec - (long long)d_out * kBlock;
+  const unsigned long long v[kCntSlots] = {
+      n_rej, n_hit, 0ull, n_acc,
+      (unsigned long long)steps + (unsigned long long)skipped + (unsigned long long)deep_ref,
+      p_pts, p_inc, (unsigned long long)steps + (unsigned long long)deep_exec, n_cyc, n_exact};
 #pragma unroll 1
   for (int k = 0; k < kCntSlots; k++) {
     if (k == kCntTooEarly) continue;  // derived on the host: candidates - the other classes
     unsigned long long x = v[k];
-    if (k == kCntEscapeIters) x += e_ref2;
-    if (k == kCntExecuted) x += e_exec2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
     if (lane_id() == 0 && x) atomicAdd(counters + k, x);
@@ -400,9 +458,10 @@ __device__ __noinline__ void flush_values(unsigned long long *counters, uint32_t
 
 __device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long *counters) {
   flush_values(counters, ws.n_rej, ws.n_hit, ws.n_acc, ws.steps, ws.skipped, ws.p_pts, ws.p_inc,
-               ws.wasted, ws.n_cyc, ws.n_exact);
+               ws.d_rounds, ws.d_out, ws.n_cyc, ws.n_exact);
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.d_out = ws.p_pts = ws.p_inc = 0;
+  ws.d_rounds = 0;
 }
 
 // Adds v (summed over the warp) to one per-channel accumulator; called from rare branches only.
@@ -433,10 +492,11 @@ __device__ __forceinline__ int push_slot(int &height, bool pred) {
   return slot;
 }
 
-__device__ __forceinline__ void push_z(ZStack &st, int &height, bool pred, double cx, double cy,
+template <bool kDown>
+__device__ __forceinline__ void push_z(WarpQueues &q, int &height, bool pred, double cx, double cy,
                                        double x, double y, int it) {
-  int slot = push_slot(height, pred);
-  if (pred) { st.c[slot] = make_double2(cx, cy); st.z[slot] = make_double2(x, y); st.it[slot] = it; }
+  const int slot = slot_of<kDown, kZCap>(push_slot(height, pred));
+  if (pred) { q.z_c[slot] = make_double2(cx, cy); q.z_z[slot] = make_double2(x, y); q.z_it[slot] = it; }
 }
 
 // Band (+1; 0 = no channel) that an escape at step `it` (1-based count, it <= max_it) falls into.
@@ -480,7 +540,7 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
     }
     n |= (int)((code - 1u) << kOrbStepBits);
   }
-  push_z(q.orb, ws.orb_n, acc, cx, cy, cx, cy, n);
+  push_z<kOrb>(q, ws.orb_n, acc, cx, cy, cx, cy, n);
 }
 
 // Fused render: a sample ESCAPED at step it_f.  Channels whose limit lies below it_f count it as
@@ -529,7 +589,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
   const int allowed = max(0, min(kGenSteps, p.max_it));  // IterateMandelbrot stops at max
   const bool may_accept = kGenSteps - 1 >= p.min_it;
 #pragma unroll 1
-  while (ws.t1_n < 32 && ws.orb_n < 32) {
+  while (ws.t1_n < 32 && ws.orb_n < 32 && ws.late_n + ws.orb_n <= kZJoint) {
     if (ws.chunk_off >= ws.chunk_len) {
       if (ws.exhausted) break;
       // The per-lane counters go to global memory when one of them nears 2^30 (and at the end
@@ -537,7 +597,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
       // measurable once the L2 is busy with reductions that miss (10000x10000: +25..70 %).
       {
         uint32_t any = ws.n_rej | ws.n_hit | ws.n_acc | ws.n_cyc | ws.n_exact | ws.steps |
-                       ws.skipped | ws.wasted | ws.p_pts | ws.p_inc;
+                       ws.skipped | ws.d_out | ws.p_pts | ws.p_inc | (uint32_t)abs(ws.d_rounds);
 #pragma unroll
         for (int k = 0; k < kMaxBands; k++) any |= ws.ch_inc[k];
         if (__ballot_sync(kFull, (any >> 29) != 0u)) {
@@ -570,8 +630,8 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     if (kCommon) {
       ws.steps += cand ? 1u : 0u;
       ws.steps += in1 ? 1u : 0u;
-      int slot = push_slot(ws.t1_n, in2);
-      if (in2) q.t1.c[slot] = make_double2(cx, cy);
+      const int slot = slot_of<kT1, kCCap>(push_slot(ws.t1_n, in2));
+      if (in2) q.c_c[slot] = make_double2(cx, cy);
       if (may_accept) push_orbit<kVar>(p, q, ws, counters, cand && !in2, cx, cy, in1 ? 2 : 1);
     } else {
       // max_it <= 2: escapes after the limit do not count; whoever is left has hit max
@@ -587,14 +647,14 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
 
 __device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pred, double cx,
                                           double cy, double x, double y, double rx, double ry,
-                                          int it, unsigned age) {
+                                          unsigned last, unsigned age) {
   unsigned m = __ballot_sync(kFull, pred);
   if (m == 0u) return;
   int slot = ws.deep_n + __popc(m & lanemask_lt());
   ws.deep_n += __popc(m);
   if (pred) {
-    q.deep.c[slot] = make_double2(cx, cy); q.deep.z[slot] = make_double2(x, y);
-    q.deep.r[slot] = make_double2(rx, ry); q.deep.meta[slot] = make_uint2((unsigned)it, age);
+    q.deep_c[slot] = make_double2(cx, cy); q.deep_z[slot] = make_double2(x, y);
+    q.deep_r[slot] = make_double2(rx, ry); q.deep_meta[slot] = make_uint2(last, age);
   }
 }
 
@@ -603,13 +663,12 @@ __device__ __forceinline__ void push_deep(WarpQueues &q, WarpState &ws, bool pre
 // per-step test.  kToLate = false: survivors go to t2 as c only; true: to `late` with their state.
 template <int kVar, int A, int N, bool kToLate>
 __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                           CStack &src, int &src_n,
-                                           unsigned long long *counters) {
+                                           int &src_n, unsigned long long *counters) {
   const int take = min(src_n, 32);
   const bool act = (int)lane_id() < take;
   src_n -= take;
   double2 c = make_double2(0.0, 0.0);
-  if (act) c = src.c[src_n + (int)lane_id()];
+  if (act) c = q.c_c[slot_of<kToLate ? kT2 : kT1, kCCap>(src_n + (int)lane_id())];
   const double cx = c.x, cy = c.y;
   double x = cx, y = cy;
 #pragma unroll
@@ -621,10 +680,10 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
     // the common case: every step counts, survivors move on
     ws.steps += (uint32_t)cnt;
     if (kToLate) {
-      push_z(q.late, ws.late_n, alive, cx, cy, x, y, A + N);
+      push_z<kLate>(q, ws.late_n, alive, cx, cy, x, y, A + N);
     } else {
-      int slot = push_slot(ws.t2_n, alive);
-      if (alive) q.t2.c[slot] = make_double2(cx, cy);
+      const int slot = slot_of<kT2, kCCap>(push_slot(ws.t2_n, alive));
+      if (alive) q.c_c[slot] = make_double2(cx, cy);
     }
     if (A + N - 1 >= p.min_it) push_orbit<kVar>(p, q, ws, counters, act && !alive, cx, cy, A + cnt);
   } else {
@@ -650,9 +709,9 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
   int it = 0;
   if (act) {
-    const int slot = ws.late_n + (int)lane_id();
-    double2 c = q.late.c[slot], z = q.late.z[slot];
-    cx = c.x; cy = c.y; x = z.x; y = z.y; it = q.late.it[slot];
+    const int slot = slot_of<kLate, kZCap>(ws.late_n + (int)lane_id());
+    double2 c = q.z_c[slot], z = q.z_z[slot];
+    cx = c.x; cy = c.y; x = z.x; y = z.y; it = q.z_it[slot];
   }
   __syncwarp();  // the slots are re-used by the pushes below
   const bool deep_room = ws.deep_n < 32;
@@ -670,10 +729,21 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   channel_finish<kVar>(p, counters, esc, it + cnt);
   const bool cont = surv && !hit;
   if (__ballot_sync(kFull, cont)) {
+    // samples well inside a period-3 component never escape: hit max without iterating
+    bool cont2 = cont;
+    if ((kVar & kVarShip) == 0 && p.shortcut) {
+      const bool p3 = cont && in_period3_component(cx, cy);
+      ws.n_hit += p3 ? 1u : 0u;
+      ws.n_cyc += p3 ? 1u : 0u;
+      ws.skipped += p3 ? (uint32_t)(p.max_it - nit) : 0u;
+      cont2 = cont && !p3;
+    }
     // deep's no-re-entry argument needs |c| <= 1.99937, and a full unchecked round must fit
-    const bool todeep = cont && deep_room && norm4(cx, cy) <= 15.99 && nit + kBlock <= p.max_it;
-    push_deep(q, ws, todeep, cx, cy, x, y, x, y, nit, 0u);
-    push_z(q.late, ws.late_n, cont && !todeep, cx, cy, x, y, nit);
+    const bool todeep = cont2 && deep_room && norm4(cx, cy) <= 15.99 && nit + kBlock <= p.max_it;
+    // meta = (last, age): after `last` rounds fewer than kBlock steps are left below max_it
+    push_deep(q, ws, todeep, cx, cy, x, y, x, y, (unsigned)(p.max_it - nit) / kBlock, 0u);
+    push_z<kLate>(q, ws.late_n, cont2 && !todeep, cx, cy, x, y, nit);
+    if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);  // (huge -m)
   }
   __syncwarp();
 }
@@ -693,81 +763,84 @@ __device__ __forceinline__ bool checkpoint_age(unsigned age) {
 // |c| <= 2 here, an orbit that leaves the radius-2 disc cannot re-enter it,
 // so "escaped somewhere in the round" <=> "outside at the end of the round".  A state that
 // repeats bit-for-bit proves the orbit periodic, i.e. it never escapes (exact shortcut).
+//
+// Every sample in `late` and `deep` has done kT2End + j * kBlock iterations (tier 2 ends at
+// kT2End; late batches and deep rounds are kBlock steps long), so a deep entry only carries
+// (last, age): it has done m24 - (last - age) * kBlock iterations, m24 = the largest such count
+// <= max_it.  The handling of finished lanes runs after ~45 % of the rounds (32 lanes, ~50 rounds
+// per sample), so it is kept short: no per-lane iteration counters (see WarpState::d_rounds), and
+// finished lanes keep iterating on stale values, which nothing reads (`act` guards every use; a
+// stale orbit may run to inf/NaN, which costs nothing on this hardware).
 template <int kVar>
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            bool drain, unsigned long long *counters) {
+  static_assert(kLateSteps == kBlock, "late batches and deep rounds must have the same length");
   const int max_it = p.max_it;
+  const int m24 = max_it - (max_it - kT2End) % kBlock;
   const bool shortcut = p.shortcut != 0;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
-  int it0 = 0;          // iterations done when this lane's sample was loaded ...
-  unsigned age0 = 0;    // ... and its age then: it = it0 + (age - age0) * kBlock
-  unsigned age = 0;     // rounds this sample has spent in deep (Brent checkpoint schedule)
+  unsigned age = 0;     // rounds this sample has spent in deep (checkpoint schedule)
   unsigned last = 0;    // the age after which no further full round fits below max_it
 #pragma unroll 1
   for (;;) {
-    if (ws.late_n >= 32) break;  // keep room for 32 hand-backs
-    if (ws.deep_n > 0 && __ballot_sync(kFull, !act)) {
-      unsigned m = __ballot_sync(kFull, !act);
-      int rank = __popc(m & lanemask_lt());
+    // keep room for 32 hand-backs
+    if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint) break;
+    const unsigned idle = __ballot_sync(kFull, !act);
+    if (ws.deep_n > 0 && idle != 0u) {
+      const int rank = __popc(idle & lanemask_lt());
       if (!act && rank < ws.deep_n) {
         const int slot = ws.deep_n - 1 - rank;
-        double2 c = q.deep.c[slot], z = q.deep.z[slot], r = q.deep.r[slot];
-        uint2 meta = q.deep.meta[slot];
+        const double2 c = q.deep_c[slot], z = q.deep_z[slot], r = q.deep_r[slot];
+        const uint2 meta = q.deep_meta[slot];
         cx = c.x; cy = c.y; x = z.x; y = z.y; rx = r.x; ry = r.y;
-        it0 = (int)meta.x; age0 = age = meta.y;
-        last = age0 + (unsigned)(max_it - it0) / kBlock;  // >= age0 + 1 (it0 + kBlock <= max)
+        last = meta.x; age = meta.y;  // last >= age + 1
+        ws.d_rounds -= (int32_t)age;
         act = true;
       }
-      ws.deep_n -= min(__popc(m), ws.deep_n);
+      ws.deep_n -= min(__popc(idle), ws.deep_n);
       __syncwarp();
     }
-    unsigned am = __ballot_sync(kFull, act);
+    const unsigned am = __ballot_sync(kFull, act);
     if (am == 0u) break;
     if (!drain && __popc(am) < kDeepExit) break;
 
     // rounds without bookkeeping until some lane needs attention
     double x0, y0;
-    bool out, same_x, tail;
+    bool out, same_x;
 #pragma unroll 1
-    for (;;) {
+    do {
+      // the checkpoint a lane is due after `age` rounds, taken before the next round (also the
+      // one still pending when a lane was suspended)
+      if (checkpoint_age(age)) { rx = x; ry = y; }
       x0 = x; y0 = y;
 #pragma unroll
       for (int k = 0; k < kBlock; k++) BUDDHA_ZSTEP(x, y, cx, cy);
       out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
       age++;
       same_x = shortcut && __double_as_longlong(x) == __double_as_longlong(rx);
-      tail = age == last;
-      const bool fin = act && (out || same_x || tail);
-      if (__ballot_sync(kFull, fin)) break;
-      if (checkpoint_age(age)) { rx = x; ry = y; }
-    }
+    } while (__ballot_sync(kFull, act && (out || same_x || age == last)) == 0u);
     {
-      // the checkpoint update of the final round was skipped by the break: compare first
       const bool cyc = same_x && __double_as_longlong(y) == __double_as_longlong(ry);
-      if (checkpoint_age(age)) { rx = x; ry = y; }
-      const bool fin = act && (out || cyc || tail);
-      int it = it0 + (int)((age - age0) * kBlock);
-      if (fin && out) { x = x0; y = y0; it -= kBlock; }  // hand back the round-start state
+      const bool fin = act && (out || cyc || age == last);
+      const int it = m24 - (int)(last - age) * kBlock;    // iterations done at the end of this round
       const bool hit = fin && !out && (cyc || it >= max_it);  // periodic, or ran all max iterations
-      const bool back = fin && !hit;                    // escaped in the round, or a short tail
-      ws.steps += fin ? (uint32_t)(it - it0) : 0u;
-      ws.wasted += (fin && out) ? (uint32_t)kBlock : 0u;
+      const bool back = fin && !hit;                      // escaped in the round, or a short tail
+      ws.d_rounds += fin ? (int32_t)age : 0;
+      ws.d_out += (fin && out) ? 1u : 0u;
       ws.skipped += hit ? (uint32_t)(max_it - it) : 0u;
       ws.n_hit += hit ? 1u : 0u;
       ws.n_cyc += (hit && it < max_it) ? 1u : 0u;
-      if (__ballot_sync(kFull, back)) push_z(q.late, ws.late_n, back, cx, cy, x, y, it);
-      if (fin) { act = false; cx = cy = x = y = rx = ry = 0.0; it0 = 0; age = age0 = 0; last = 0; }
-      // the per-lane 32-bit counters are flushed at every cursor grab; with a very large -m a few
-      // never-escaping samples could wrap them before that
-      if (__ballot_sync(kFull, ((ws.steps | ws.skipped) >> 30) != 0u)) flush_counters(ws, counters);
+      // an escaped sample goes back to `late` with its round-start state
+      if (__ballot_sync(kFull, back))
+        push_z<kLate>(q, ws.late_n, back, cx, cy, out ? x0 : x, out ? y0 : y, out ? it - kBlock : it);
+      act = act && !fin;
+      // with a very large -m a few never-escaping samples could wrap the 32-bit counter
+      if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);
     }
   }
-  {
-    int it = it0 + (int)((age - age0) * kBlock);
-    ws.steps += act ? (uint32_t)(it - it0) : 0u;
-    push_deep(q, ws, act, cx, cy, x, y, rx, ry, it, age);  // keeps the checkpoint and its schedule
-  }
+  ws.d_rounds += act ? (int32_t)age : 0;
+  push_deep(q, ws, act, cx, cy, x, y, rx, ry, last, age);  // keeps the checkpoint and its schedule
   __syncwarp();
 }
 
@@ -857,10 +930,10 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
       unsigned m = __ballot_sync(kFull, !o.act);
       int rank = __popc(m & lanemask_lt());
       if (!o.act && rank < ws.orb_n) {
-        const int slot = ws.orb_n - 1 - rank;
+        const int slot = slot_of<kOrb, kZCap>(ws.orb_n - 1 - rank);
         orbit_credit<kVar>(o, ws);
-        double2 c = q.orb.c[slot], z = q.orb.z[slot];
-        o.cx = c.x; o.cy = c.y; o.x = z.x; o.y = z.y; o.n = q.orb.it[slot];
+        double2 c = q.z_c[slot], z = q.z_z[slot];
+        o.cx = c.x; o.cy = c.y; o.x = z.x; o.y = z.y; o.n = q.z_it[slot];
         o.act = true;
       }
       ws.orb_n -= min(__popc(m), ws.orb_n);
@@ -872,7 +945,7 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     orbit_step<kVar>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
   orbit_credit<kVar>(o, ws);
-  if (__ballot_sync(kFull, o.act)) push_z(q.orb, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
+  if (__ballot_sync(kFull, o.act)) push_z<kOrb>(q, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
   __syncwarp();
 }
 
@@ -905,7 +978,8 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   ws.chunk_off = ws.chunk_len = 0;
   ws.exhausted = false;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.d_out = ws.p_pts = ws.p_inc = 0;
+  ws.d_rounds = 0;
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
@@ -916,16 +990,16 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     // dry, upstream first.
     const bool dry = ws.exhausted && ws.chunk_off >= ws.chunk_len;
     const bool dry1 = dry && ws.t1_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
-    if (ws.orb_n >= 32) {
+    if (ws.orb_n >= 32 || (ws.orb_n >= kOrbExit && ws.late_n + ws.orb_n > kZJoint)) {
       orbit_phase<kVar>(p, q, ws, sink);
-    } else if (ws.late_n >= 32 || (dry2 && ws.late_n > 0)) {
+    } else if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint || (dry2 && ws.late_n > 0)) {
       late_phase<kVar>(p, q, ws, counters);
     } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
       deep_phase<kVar>(p, q, ws, dry3, counters);
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
-      tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, q.t2, ws.t2_n, counters);
+      tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, ws.t2_n, counters);
     } else if (ws.t1_n >= 32 || (dry && ws.t1_n > 0)) {
-      tier_phase<kVar, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, q.t1, ws.t1_n, counters);
+      tier_phase<kVar, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, ws.t1_n, counters);
     } else if (!dry) {
       if (p.max_it > kGenSteps) gen_phase<kVar, true>(p, q, ws, cursor, counters);
       else gen_phase<kVar, false>(p, q, ws, cursor, counters);
@@ -941,8 +1015,9 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     for (int k = lane_id(); k < ws.orb_n; k += 32) {
       unsigned dst = base + k;
       if (dst < spill.capacity) {
-        spill.entries[dst] = make_double4(q.orb.c[k].x, q.orb.c[k].y, q.orb.z[k].x, q.orb.z[k].y);
-        spill.steps[dst] = q.orb.it[k];
+        const int slot = slot_of<kOrb, kZCap>(k);
+        spill.entries[dst] = make_double4(q.z_c[slot].x, q.z_c[slot].y, q.z_z[slot].x, q.z_z[slot].y);
+        spill.steps[dst] = q.z_it[slot];
       }
     }
   }
@@ -976,7 +1051,8 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   tile_counters_load(p, sink, false);  // continue the lists where the render kernel stopped
   WarpState ws;
   ws.n_rej = ws.n_hit = ws.n_acc = ws.n_cyc = ws.n_exact = 0;
-  ws.steps = ws.skipped = ws.wasted = ws.p_pts = ws.p_inc = 0;
+  ws.steps = ws.skipped = ws.d_out = ws.p_pts = ws.p_inc = 0;
+  ws.d_rounds = 0;
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
@@ -1067,6 +1143,45 @@ channel_sum_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict
       if ((bands >> b) & 1u) v += hist[(size_t)b * cells + i];
     out[i] = v;
   }
+}
+
+// ---- histogram digest -----------------------------------------------------------------------
+//
+// A digest that can be formed in parallel, for "N GPUs == 1 GPU" checks on 1.6 GB histograms
+// without moving them to the host: cells are taken in blocks of kDigestBlock = 4096; inside a
+// block, lane l (0..31) folds cells l, l + 32, l + 64, ... with 64-bit FNV-1a on whole cells
+// (h = (h ^ cell) * prime from the FNV offset basis; cells past the end count as 0), the 32 lane
+// values are folded the same way in lane order into the block digest, and the host folds the
+// block digests in block order.  The tests restate it in numpy (blocked_fnv).
+constexpr int kDigestBlock = 4096;
+constexpr unsigned long long kFnvBasis = 0xcbf29ce484222325ull, kFnvPrime = 0x100000001b3ull;
+
+__global__ void __launch_bounds__(256)
+digest_blocks_kernel(const uint32_t *__restrict__ hist, size_t cells,
+                     unsigned long long *__restrict__ block_digest, size_t n_blocks) {
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  for (size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
+    const size_t base = b * kDigestBlock;
+    unsigned long long h = kFnvBasis;
+#pragma unroll 4
+    for (int k = 0; k < kDigestBlock / 32; k++) {
+      const size_t i = base + (size_t)k * 32 + lane;
+      const uint32_t v = i < cells ? __ldg(hist + i) : 0u;
+      h = (h ^ v) * kFnvPrime;
+    }
+    unsigned long long d = kFnvBasis;
+    for (int l = 0; l < 32; l++) d = (d ^ __shfl_sync(kFull, h, l)) * kFnvPrime;
+    if (lane == 0) block_digest[b] = d;
+  }
+}
+
+// dst[i] += src[i] (mod 2^32): merges counts that were copied to the device into a histogram.
+__global__ void __launch_bounds__(256)
+add_cells_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t cells) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
+    dst[i] += src[i];
 }
 
 // ---- tone-map (cudabrot.cu:416-468) ----------------------------------------------------------

@@ -324,6 +324,24 @@ static void SidecarName(char *dst, size_t n) { snprintf(dst, n, "%s.cursor", g.i
 static void LoadInProgressBuffer(void) {
   if (!g.inprogress_file) return;
   uint64_t expected_size = ImageBufferSize();
+  if (Channels() > 1) {
+    /* all channel files or none: loading a partial set would restart the sample stream and the
+     * save at the end would overwrite the channels that do exist */
+    int present = 0;
+    char missing[4096] = "";
+    for (int k = 0; k < Channels(); k++) {
+      char file[4096];
+      ChannelFileName(file, sizeof(file), g.inprogress_file, k, 0);
+      if (access(file, F_OK) == 0) present++;
+      else if (!missing[0]) snprintf(missing, sizeof(missing), "%s", file);
+    }
+    if (present != 0 && present != Channels()) {
+      printf("Only %d of the %d channel files of %s exist (%s is missing). Not overwriting them.\n",
+        present, Channels(), g.inprogress_file, missing);
+      Cleanup();
+      exit(1);
+    }
+  }
   for (int k = 0; k < Channels(); k++) {
     char file[4096];
     ChannelFileName(file, sizeof(file), g.inprogress_file, k, 0);

@@ -27,6 +27,10 @@ class Renderer:
         p.max_iterations, p.min_iterations = max_iterations, min_iterations
         p.seed, p.flags = seed, flags
         self.channels = list(channels) if channels else None
+        if self.channels is not None and len(self.channels) == 1:
+            # (one pair would silently fall back to max_iterations / min_iterations)
+            raise ValueError("channels needs 2..%d (max, min) pairs; use max_iterations / "
+                             "min_iterations for a single channel" % capi.MAX_CHANNELS)
         if self.channels:
             p.n_channels = len(self.channels)
             for k, (m, c) in enumerate(self.channels[:capi.MAX_CHANNELS]):
@@ -93,10 +97,13 @@ class Renderer:
     def sync(self):
         self._check(self._lib.buddha_sync(self._ctx))
 
-    def render_seconds(self, seconds, first=0):
+    def render_seconds(self, seconds, first=0, stop=None):
+        """stop: an optional ctypes.c_int another thread may set to end the run (the reference's
+        quit_signal_received, cudabrot.cu:483); required when seconds < 0."""
         done, passes = C.c_uint64(), C.c_uint64()
-        self._check(self._lib.buddha_render_seconds(self._ctx, seconds, None, first,
-                                                    C.byref(done), C.byref(passes)))
+        self._check(self._lib.buddha_render_seconds(self._ctx, seconds,
+                                                    C.byref(stop) if stop is not None else None,
+                                                    first, C.byref(done), C.byref(passes)))
         return done.value, passes.value
 
     def last_render_ms(self):
@@ -135,6 +142,40 @@ class Renderer:
         ms = C.c_float()
         self._check(self._lib.buddha_last_tonemap_ms(self._ctx, C.byref(ms)))
         return ms.value
+
+    # -- overlapped host transfers (no reference equivalent: its copies block) ----------------
+    def add_histogram_async(self, hist):
+        """Adds host counts to the histogram; the copy overlaps whatever is rendering.  `hist`
+        must stay alive (and should be page-locked) until sync()."""
+        if hist.dtype != np.uint32 or not hist.flags["C_CONTIGUOUS"]:
+            raise TypeError("add_histogram_async needs a C-contiguous uint32 array (no copy is made)")
+        self._check(self._lib.buddha_add_histogram_async(self._ctx, hist.ctypes.data, hist.size))
+
+    def snapshot(self):
+        self._check(self._lib.buddha_snapshot(self._ctx))
+
+    def read_snapshot(self, out=None):
+        if out is None:
+            shape = (self.height, self.width)
+            out = np.empty(((self.n_channels,) + shape) if self.channels else shape, dtype=np.uint32)
+        self._check(self._lib.buddha_read_snapshot(self._ctx, out.ctypes.data, out.size))
+        return out
+
+    def tonemap_snapshot(self, gamma=1.0, big_endian=False, out=None, channel=0):
+        """Returns (uint16 image, max, scale) of the snapshot."""
+        mx, sc = C.c_uint32(), C.c_double()
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.uint16)
+        self._check(self._lib.buddha_tonemap_snapshot_u16(self._ctx, channel, gamma,
+                                                          int(big_endian), out.ctypes.data,
+                                                          out.size, C.byref(mx), C.byref(sc)))
+        return out, mx.value, sc.value
+
+    def digest(self, channel=0):
+        """64-bit blocked FNV-1a digest of one channel, formed on the GPU (include/buddha.h)."""
+        d = C.c_uint64()
+        self._check(self._lib.buddha_histogram_digest(self._ctx, channel, C.byref(d)))
+        return d.value
 
     # -- multi-GPU plumbing --------------------------------------------------------------------
     @property

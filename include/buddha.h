@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BUDDHA_ABI_VERSION 2
+#define BUDDHA_ABI_VERSION 3
 #define BUDDHA_MAX_CHANNELS 4
 
 enum {
@@ -168,6 +168,34 @@ int buddha_tonemap_channel_u16(buddha_ctx *ctx, int channel, double gamma, int b
 
 /* Device time of the most recent tone-map kernels (max-reduce + map), in ms. */
 int buddha_last_tonemap_ms(buddha_ctx *ctx, float *ms);
+
+/* Overlapped host transfers.  The reference's copies (H2D cudabrot.cu:256-257, D2H :496-497) block
+ * and its tone-map runs on the host while the GPU idles (:500); these calls let a long job stream
+ * results out, and saved counts in, while the next sample range renders:
+ *   buddha_add_histogram_async  ADDS host counts (a saved -s buffer, cells as for load_histogram)
+ *       to the histogram: the copy runs on its own stream beside whatever is rendering, the add is
+ *       ordered after the work enqueued so far.  `host` must stay valid until buddha_sync (use
+ *       page-locked memory for a truly asynchronous copy).
+ *   buddha_snapshot             freezes the histogram as of all work enqueued so far into a second
+ *       device buffer (returns at once).
+ *   buddha_read_snapshot / buddha_tonemap_snapshot_u16   the same results as buddha_read_histogram /
+ *       buddha_tonemap_channel_u16 would have given at the snapshot, delivered on a copy stream:
+ *       they block the caller, but neither wait for nor delay renders enqueued after the snapshot. */
+int buddha_add_histogram_async(buddha_ctx *ctx, const uint32_t *host, size_t cells);
+int buddha_snapshot(buddha_ctx *ctx);
+int buddha_read_snapshot(buddha_ctx *ctx, uint32_t *host, size_t cells);
+int buddha_tonemap_snapshot_u16(buddha_ctx *ctx, int channel, double gamma, int big_endian,
+                                uint16_t *host_out, size_t cells, uint32_t *max_out,
+                                double *scale_out);
+
+/* 64-bit digest of one channel of the histogram (channel 0 of a plain context), formed on the GPU:
+ * equal histograms give equal digests, so "N GPUs == 1 GPU == CPU restatement" can be checked on 1.6 GB
+ * canvases without moving them.  Definition (restated in numpy by the tests, blocked_fnv):
+ * blocks of 4096 cells; in a block, lane l = 0..31 folds cells l, l+32, ... with FNV-1a-64 taken
+ * over whole cells (h = (h ^ cell) * 0x100000001b3 from 0xcbf29ce484222325; cells past the end are
+ * 0); the 32 lane values are folded the same way into the block digest, the block digests into the
+ * result. */
+int buddha_histogram_digest(buddha_ctx *ctx, int channel, uint64_t *digest);
 
 /* Multi-GPU plumbing (no reference equivalent; cudabrot is single-GPU).
  * Raw device pointer + CUDA stream of this context, so a host framework (torch.distributed / NCCL)

@@ -495,3 +495,45 @@ uint64_t oracle_check_fast_bin(const oracle_dims *d, const double *points, uint6
   if (in_canvas) *in_canvas = in;
   return bad;
 }
+
+/* The kernel's conservative period-3 test (buddha_kernels.cuh: in_period3_component), restated in
+ * float arithmetic: lambda = 8 + 4c -+ 4c sqrt(-7 - 4c) from the Giarrusso-Fisher relation
+ * c^3 + 2c^2 + (1 - lambda/8)c + (1 - lambda/8)^2 = 0; 1 if min |lambda|^2 < limit. */
+int oracle_period3_flag(double c_real, double c_imag, float limit) {
+  const float a = (float)c_real, b = (float)c_imag;
+  const float wr = fmaf(-4.0f, a, -7.0f), wi = -4.0f * b;
+  const float mw = sqrtf(fmaf(wr, wr, wi * wi));
+  const float sr = sqrtf(fmaxf(0.5f * (mw + wr), 0.0f));
+  const float si = copysignf(sqrtf(fmaxf(0.5f * (mw - wr), 0.0f)), wi);
+  const float tr = fmaf(a, sr, -b * si), ti = fmaf(a, si, b * sr);
+  const float br = fmaf(4.0f, a, 8.0f), bi = 4.0f * b;
+  const float l1r = fmaf(-4.0f, tr, br), l1i = fmaf(-4.0f, ti, bi);
+  const float l2r = fmaf(4.0f, tr, br), l2i = fmaf(4.0f, ti, bi);
+  const float m1 = fmaf(l1r, l1r, l1i * l1i), m2 = fmaf(l2r, l2r, l2i * l2i);
+  return fminf(m1, m2) < limit;
+}
+
+/* Evidence for the claim the kernel relies on: every sample the period-3 test flags runs the
+ * reference's escape loop (cudabrot.cu:319-340) to max_iterations.  Returns the number of flagged
+ * samples that escaped (must be 0); *flagged / *inset count the flagged samples and all samples
+ * that hit max_iterations after passing the cardioid / bulb test. */
+uint64_t oracle_check_period3(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                              float limit, uint64_t *flagged, uint64_t *inset) {
+  uint64_t bad = 0, fl = 0, in = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : bad, fl, in)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    if (oracle_rejected(cre, cim)) continue;
+    int f = oracle_period3_flag(cre, cim, limit);
+    if (!f && inset == NULL) continue;
+    int it = oracle_escape_iterations(cre, cim, max_iterations);
+    if (it >= max_iterations) in++;
+    if (f) { fl++; if (it < max_iterations) bad++; }
+  }
+  if (flagged) *flagged = fl;
+  if (inset) *inset = in;
+  return bad;
+}

@@ -127,6 +127,13 @@ uint64_t oracle_check_scaled(uint64_t seed, uint64_t first, uint64_t count, int 
 uint64_t oracle_check_fast_bin(const oracle_dims *d, const double *points, uint64_t n,
                                uint64_t *exact_count, uint64_t *in_canvas);
 
+/* The kernel's conservative period-3 membership test restated in float arithmetic, and the check
+ * that every sample it flags runs the reference's escape loop to max_iterations (returns the number
+ * that did not: must be 0). */
+int oracle_period3_flag(double c_real, double c_imag, float limit);
+uint64_t oracle_check_period3(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                              float limit, uint64_t *flagged, uint64_t *inset);
+
 #ifdef __cplusplus
 }
 #endif

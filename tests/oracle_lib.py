@@ -167,6 +167,41 @@ def fnv1a64(hist):
     return int(lib().oracle_fnv1a64(_p(h, C.c_uint32), h.size))
 
 
+def blocked_fnv(hist):
+    """The digest buddha_histogram_digest forms on the GPU (include/buddha.h), restated in numpy:
+    blocks of 4096 cells; lane l = 0..31 of a block folds cells l, l+32, ... with FNV-1a-64 over
+    whole cells; the 32 lane values fold into the block digest, the block digests into the result."""
+    basis, prime = np.uint64(0xcbf29ce484222325), np.uint64(0x100000001b3)
+    cells = np.ascontiguousarray(hist, dtype=np.uint32).reshape(-1)
+    n_blocks = (cells.size + 4095) // 4096
+    padded = np.zeros(n_blocks * 4096, dtype=np.uint64)
+    padded[:cells.size] = cells
+    v = padded.reshape(n_blocks, 128, 32)
+    with np.errstate(over="ignore"):
+        h = np.full((n_blocks, 32), basis, dtype=np.uint64)
+        for k in range(128):
+            h = (h ^ v[:, k, :]) * prime
+        d = np.full(n_blocks, basis, dtype=np.uint64)
+        for l in range(32):
+            d = (d ^ h[:, l]) * prime
+        out = basis
+        for b in range(n_blocks):
+            out = (out ^ d[b]) * prime
+    return int(out)
+
+
+def check_period3(seed, first, count, max_iter, limit=0.96):
+    """(flagged samples that escaped -- must be 0, flagged, all never-escaping samples): the evidence
+    behind the kernel's conservative period-3 test (buddha_kernels.cuh: in_period3_component)."""
+    L = lib()
+    L.oracle_check_period3.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_float,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.oracle_check_period3.restype = C.c_uint64
+    fl, ins = C.c_uint64(), C.c_uint64()
+    bad = L.oracle_check_period3(seed, first, count, max_iter, limit, C.byref(fl), C.byref(ins))
+    return int(bad), fl.value, ins.value
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

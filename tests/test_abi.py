@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(buddha):
     L = buddha.capi.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.buddha_abi_version() == 2
+    assert L.buddha_abi_version() == 3
 
 
 def test_no_torch_or_oracle_dependency(buddha):

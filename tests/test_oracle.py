@@ -190,3 +190,16 @@ def test_tonemap_max_pixel_quirk(oracle):
     assert mx == 372 and int(img[0, 2]) == 65534
     img, _, _ = oracle.tonemap(h, 2.2)
     assert int(img[0, 2]) == 65535
+
+
+def test_period3_component_test_is_conservative(oracle):
+    """The kernel skips the escape loop for samples whose period-3 multiplier (closed form,
+    Giarrusso & Fisher) has |lambda|^2 < 0.96.  Every such sample must run the reference's loop
+    (cudabrot.cu:319-340) to max_iterations; a limit beyond the component boundary (|lambda| = 1)
+    must be caught by this very check."""
+    for seed, first in ((1337, 0), (99, 1 << 40)):
+        bad, flagged, inset = oracle.check_period3(seed, first, 1 << 22, 20000)
+        assert bad == 0
+        assert 0.35 < flagged / inset < 0.46          # period-3 components: ~42 % of what is left
+    bad, _, _ = oracle.check_period3(1337, 0, 1 << 22, 20000, limit=1.05)
+    assert bad > 0

@@ -444,3 +444,191 @@ def test_in_process_multi_gpu_merge(buddha, oracle):
     assert np.array_equal(rs[0].read_histogram(), ohist)
     for r in rs:
         r.close()
+
+
+def test_in_process_fused_merge_and_tonemap_on_other_device(buddha, oracle):
+    """A fused context on device 1 must tone-map there even while device 0 is current, and
+    buddha_merge must leave the caller's device alone (round-1 review: the channel assembly ran
+    before cudaSetDevice).  Channels are compared with separate oracle runs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    chans = [(100, 20), (1000, 20)]
+    n = 1 << 19
+    rs = [buddha.Renderer(300, 200, channels=chans, device=d) for d in (1, 0)]   # root on device 1
+    rs[0].render_samples(0, n // 2)
+    rs[1].render_samples(n // 2, n - n // 2)
+    torch.cuda.set_device(0)
+    buddha.merge_in_process(rs, root=0)
+    assert torch.cuda.current_device() == 0
+    for k, (m, c) in enumerate(chans):
+        ohist, _, _ = oracle.render(300, 200, m, c, 1337, 0, n)
+        oimg, omx, oscale = oracle.tonemap(ohist, 2.2, big_endian=True)
+        img, mx, scale = rs[0].tonemap(2.2, big_endian=True, channel=k)   # device 0 is current
+        assert (mx, scale) == (omx, oscale) and np.array_equal(img, oimg)
+        assert np.array_equal(rs[0].read_channel(k), ohist)
+    # contexts that do not describe the same canvas / channels are refused
+    other = buddha.Renderer(300, 200, channels=[(100, 20), (999, 20)], device=0)
+    with pytest.raises(buddha.BuddhaError):
+        buddha.merge_in_process([rs[0], other], root=0)
+    for r in rs + [other]:
+        r.close()
+
+
+def test_histogram_digest_matches_numpy_restatement(buddha, oracle):
+    """buddha_histogram_digest (blocked FNV-1a-64 formed on the GPU) == the numpy restatement over
+    the oracle's histogram; ragged sizes, a fused channel, and sensitivity to a single cell."""
+    for (w, h, m, c, n) in [(1000, 1000, 100, 20, 1 << 22), (333, 77, 300, 5, 100003),
+                            (64, 64, 50, 60, 1 << 12)]:
+        ohist, _, _ = oracle.render(w, h, m, c, 1337, 0, n)
+        with buddha.Renderer(w, h, m, c) as r:
+            assert r.digest() == oracle.blocked_fnv(np.zeros((h, w), dtype=np.uint32))
+            r.render_samples(0, n)
+            assert r.digest() == oracle.blocked_fnv(ohist)
+            bumped = ohist.copy()
+            bumped[h - 1, w - 1] += 1
+            r.load_histogram(bumped)
+            assert r.digest() == oracle.blocked_fnv(bumped) != oracle.blocked_fnv(ohist)
+    chans = [(100, 20), (1000, 20), (5000, 20)]
+    with buddha.Renderer(500, 400, channels=chans) as r:
+        r.render_samples(0, 1 << 20)
+        for k, (m, c) in enumerate(chans):
+            ohist, _, _ = oracle.render(500, 400, m, c, 1337, 0, 1 << 20)
+            assert r.digest(k) == oracle.blocked_fnv(ohist)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_overlapped_transfers_match_blocking_calls(buddha, oracle, fused):
+    """add_histogram_async / snapshot / read_snapshot / tonemap_snapshot (copies overlapped with
+    the next render) deliver exactly what load / read / tonemap deliver at the same point."""
+    import torch
+    w, h, n = 640, 480, 1 << 20
+    chans = [(100, 20), (1000, 20)] if fused else None
+    n_ch = 2 if fused else 1
+    rng = np.random.default_rng(11)
+    saved = torch.zeros(n_ch * h * w, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    saved[:] = rng.integers(0, 50, size=saved.size, dtype=np.uint32)
+    shape = (n_ch, h, w) if fused else (h, w)
+    expect = []
+    for (m, c) in (chans or [(300, 20)]):
+        base = saved.reshape(n_ch, h, w)[len(expect)].copy()
+        h1, _, _ = oracle.render(w, h, m, c, 1337, 0, n, hist=base.copy())
+        h2, _, _ = oracle.render(w, h, m, c, 1337, n, n, hist=h1 + base)   # saved counts added twice
+        expect.append((h1, h2))
+    with buddha.Renderer(w, h, 300, 20, channels=chans) as r:
+        with pytest.raises(buddha.BuddhaError):
+            r.read_snapshot()                       # no snapshot yet
+        r.add_histogram_async(saved.reshape(shape))
+        r.render_samples_async(0, n)
+        r.snapshot()
+        r.add_histogram_async(saved.reshape(shape))  # both enqueued behind the snapshot
+        r.render_samples_async(n, n)
+        snap = r.read_snapshot()                     # step 1, while step 2 renders
+        for k in range(n_ch):
+            got = snap[k] if fused else snap
+            assert np.array_equal(got, expect[k][0])
+            oimg, omx, oscale = oracle.tonemap(expect[k][0], 2.2, big_endian=True)
+            img, mx, scale = r.tonemap_snapshot(2.2, big_endian=True, channel=k)
+            assert (mx, scale) == (omx, oscale) and np.array_equal(img, oimg)
+        r.sync()
+        live = r.read_histogram()
+        for k in range(n_ch):
+            assert np.array_equal(live[k] if fused else live, expect[k][1])
+        with pytest.raises(buddha.BuddhaError):
+            r.add_histogram_async(np.zeros(7, dtype=np.uint32))
+
+
+def test_stop_flag_ends_an_endless_run(buddha, oracle):
+    """-t -1 semantics (cudabrot.cu:483, :756-760): the run ends at the next pass boundary once
+    the flag is set, and what was rendered is exactly the index range [0, samples_done)."""
+    import ctypes
+    import threading
+    with buddha.Renderer(200, 150, 200, 20) as r:
+        with pytest.raises(buddha.BuddhaError):
+            r.render_seconds(-1.0)                   # endless without a stop flag is refused
+        stop = ctypes.c_int(0)
+        threading.Timer(0.4, lambda: setattr(stop, "value", 1)).start()
+        done, passes = r.render_seconds(-1.0, stop=stop)
+        assert passes >= 1 and done >= 13107200
+        hist, cnt = r.read_histogram(), r.counters()
+        assert cnt["candidates"] == done
+        assert int(hist.sum(dtype=np.uint64)) == cnt["increments"]
+    with buddha.Renderer(200, 150, 200, 20) as r:   # the same range in one call: same histogram
+        r.render_samples(0, done)
+        assert np.array_equal(r.read_histogram(), hist)
+    n = 1 << 22                                      # and its prefix agrees with the oracle
+    ohist, ocnt, _ = oracle.render(200, 150, 200, 20, 1337, 0, n)
+    with buddha.Renderer(200, 150, 200, 20) as r:
+        r.render_samples(0, n)
+        assert_same(r.read_histogram(), r.counters(), ohist, ocnt)
+
+
+def test_cli_sigint_saves_state_and_exits_zero(buddha, oracle, tmp_path):
+    """bin/cudabrot -t -1: SIGINT ends the run after the current pass, the -s buffer and the PGM
+    are written, the exit code is 0 (cudabrot.cu:483, :756-760, :785), and the buffer equals the
+    oracle over [0, cursor)."""
+    import signal
+    import time
+    cli = buddha.capi.CLI_PATH
+    save, out = str(tmp_path / "state.raw"), str(tmp_path / "img.pgm")
+    p = subprocess.Popen([cli, "-w", "160", "-h", "120", "-m", "60", "-c", "5", "-t", "-1", "-s",
+                          save, "-o", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True)
+    time.sleep(2.5)
+    p.send_signal(signal.SIGINT)
+    stdout, _ = p.communicate(timeout=120)
+    assert p.returncode == 0, stdout
+    assert "Press ctrl+C to finish." in stdout and "Signal 2 received" in stdout
+    assert "Done! Output image saved: %s" % out in stdout
+    seed, nxt = open(save + ".cursor").read().split()[1::2]
+    nxt = int(nxt)
+    assert int(seed) == 1337 and nxt >= 13107200
+    got = np.fromfile(save, dtype="<u4").reshape(120, 160)
+    m = 1 << 23   # the oracle over the whole range would take minutes: a prefix bounds it from below,
+    ohist, _, _ = oracle.render(160, 120, 60, 5, 1337, 0, m)      # the library re-renders the range
+    assert np.all(got >= ohist)
+    with buddha.Renderer(160, 120, 60, 5) as r:
+        r.render_samples(0, nxt)
+        assert np.array_equal(r.read_histogram(), got)
+        r.clear()
+        r.render_samples(0, m)
+        assert np.array_equal(r.read_histogram(), ohist)
+
+
+def test_cli_refuses_partial_channel_set(buddha, tmp_path):
+    """A fused -s resume with only some of the channel files present must stop instead of
+    restarting the stream and overwriting the files that exist."""
+    cli = buddha.capi.CLI_PATH
+    save, out = str(tmp_path / "state.raw"), str(tmp_path / "img.pgm")
+    args = [cli, "-w", "64", "-h", "48", "--channels", "100:20,1000:20", "-s", save, "-o", out,
+            "--samples", "100000"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    before = open(save + ".ch0", "rb").read()
+    os.remove(save + ".ch1")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1
+    assert "Only 1 of the 2 channel files" in r.stdout
+    assert open(save + ".ch0", "rb").read() == before
+
+
+def test_production_tiles_cfg5_fused_and_cfg3_m20000(buddha, oracle):
+    """Oracle parity at the production tile size (64 MB tiles, calibration + pipeline launches):
+    BASELINE config 5 fused at 10000x10000 and config 3's canvas at -m 20000."""
+    n = 1 << 21
+    chans = [(100, 20), (1000, 20), (20000, 20)]
+    with buddha.Renderer(10000, 10000, channels=chans) as r:
+        r.render_samples(0, n)
+        for k, (m, c) in enumerate(chans):
+            ohist, ocnt, _ = oracle.render(10000, 10000, m, c, 1337, 0, n)
+            assert r.digest(k) == oracle.blocked_fnv(ohist)
+            assert np.array_equal(r.read_channel(k), ohist)
+            cc = r.channel_counters(k)
+            for key in COUNTER_KEYS:
+                assert cc[key] == ocnt[key], (k, key)
+    ohist, ocnt, _ = oracle.render(20000, 20000, 20000, 20, 1337, 0, n)
+    with buddha.Renderer(20000, 20000, 20000, 20) as r:
+        r.render_samples(0, 1 << 20)            # calibration launch + a second, pipelined call
+        r.render_samples(1 << 20, n - (1 << 20))
+        assert r.digest() == oracle.blocked_fnv(ohist)
+        assert_same(r.read_histogram(), r.counters(), ohist, ocnt)

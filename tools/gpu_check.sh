@@ -19,10 +19,10 @@ benchref)
   cat gpurun_out/bench_ref.json ;;
 ncu)
   ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-      --log-file gpurun_out/launches.csv timeout -s KILL 300 python bench.py --steps 2 --warmup 1 --skip-baselines \
+      --log-file gpurun_out/launches.csv timeout -s KILL 300 python bench.py --steps 2 --warmup 1 --skip-baselines --no-extras \
       --samples-per-step 1073741824 > gpurun_out/ncu_bench.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:render_persistent -s 1 -c 1 \
-      -f -o gpurun_out/prof_render timeout -s KILL 600 python bench.py --steps 1 --warmup 1 --skip-baselines \
+      -f -o gpurun_out/prof_render timeout -s KILL 600 python bench.py --steps 1 --warmup 1 --skip-baselines --no-extras \
       --samples-per-step 1073741824 > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log ;;
 esac

@@ -3,7 +3,7 @@
 WL=${1:-cfg3}; N=${2:-1073741824}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$WL.csv \
-  timeout -s KILL 300 python bench.py --workload $WL --steps 2 --warmup 1 --skip-baselines --samples-per-step $N > gpurun_out/launches_$WL.log 2>&1
+  timeout -s KILL 300 python bench.py --workload $WL --steps 2 --warmup 1 --skip-baselines --no-extras --samples-per-step $N > gpurun_out/launches_$WL.log 2>&1
 python - "$WL" <<'PY'
 import csv,sys
 rows=[l for l in open('gpurun_out/launches_%s.csv'%sys.argv[1]) if l.startswith('"')]

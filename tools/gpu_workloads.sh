@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/workloads.jsonl
 for wl in ${WLS:-cfg1 cfg2 cfg3 cfg3_m20000 cfg4 cfg5a cfg5b cfg5c}; do
-  timeout -s KILL 300 python bench.py --workload $wl --steps 2 --warmup 1 --skip-baselines \
+  timeout -s KILL 300 python bench.py --workload $wl --steps 2 --warmup 1 --skip-baselines --no-extras \
     --samples-per-step ${1:-4294967296} >> gpurun_out/workloads.jsonl 2>> gpurun_out/workloads.err
 done
 if [ -n "${REF:-}" ]; then
@@ -22,7 +22,7 @@ fi
 python - <<'PY'
 import json
 for l in open('gpurun_out/workloads.jsonl'):
-    d=json.loads(l); c=d['counters']; S=d['config']['samples_per_step_per_gpu']*d['steps']
+    d=json.loads(l); c=d['counters']; S=d['run']['samples_per_step_per_gpu']*d['steps']
     print("%-12s %.3e samples/s  %.3e pts/s  e2e %.3e  frac %.2f  exec/S %.1f ref/S %.1f P/S %.3f exact %.4f ms/step %.1f" % (
         d['config']['workload'].split(':')[0], d['value'], d['orbit_points_per_s'], d['e2e']['value'], d['roofline']['frac'],
         c['executed_iters']/S, c['escape_iters']/S, c['orbit_points']/S, c['exact_bins']/max(c['orbit_points'],1), d['ms_per_step']))
