@@ -38,14 +38,16 @@ FULL = (-2.0, 2.0, -2.0, 2.0)
 WORKLOADS = {
     "cfg1": (1000, 1000, 100, 20, FULL, 1 << 32),
     "cfg2": (4000, 4000, 20000, 10000, FULL, 1 << 35),
-    "cfg3": (20000, 20000, 2000, 20, FULL, 1 << 32),
+    # 1.6 GB in + 2.4 GB out per step over PCIe take ~140 ms: 2^34-sample steps (~240 ms of
+    # rendering) let the overlapped e2e pipeline hide them
+    "cfg3": (20000, 20000, 2000, 20, FULL, 1 << 34),
     "cfg3_m20000": (20000, 20000, 20000, 20, FULL, 1 << 32),
     "cfg4": (8000, 4000, 5000, 20, (0.0, 1.0, 0.0, 0.5), 1 << 32),
     "cfg5a": (10000, 10000, 100, 20, FULL, 1 << 32),
     "cfg5b": (10000, 10000, 1000, 20, FULL, 1 << 32),
     "cfg5c": (10000, 10000, 20000, 20, FULL, 1 << 32),
     # config 5 as ONE fused pass: every candidate is rendered once into the three channels
-    "cfg5": (10000, 10000, 20000, 20, FULL, 1 << 32),
+    "cfg5": (10000, 10000, 20000, 20, FULL, 1 << 33),
     # the same trio on a canvas whose three histograms fit L2 together (192 MB), fused and apart
     "cfg5_4k": (4000, 4000, 20000, 20, FULL, 1 << 32),
     "cfg5_4k_a": (4000, 4000, 100, 20, FULL, 1 << 32),

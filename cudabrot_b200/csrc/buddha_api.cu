@@ -423,7 +423,7 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
     c->spill[b].capacity = (unsigned)c->grid * kWarpsPerCta * kSpillPerWarp;
     CUC(cudaMalloc(&c->spill[b].entries, sizeof(double4) * c->spill[b].capacity));
     CUC(cudaMalloc(&c->spill[b].steps, sizeof(int) * c->spill[b].capacity));
-    CUC(cudaMalloc(&c->spill[b].count, sizeof(unsigned int) * 2));
+    CUC(cudaMalloc(&c->spill[b].count, sizeof(unsigned int) * 4));  // see OrbitSpill
     c->d_spill_next[b] = c->spill[b].count + 1;
   }
   {
@@ -606,6 +606,29 @@ int buddha_read_histogram(buddha_ctx *c, uint32_t *host, size_t cells) {
   return BUDDHA_OK;
 }
 
+// BUDDHA_TILE_TRACE=1 (experiments): device timestamps of every pipeline launch -- render start /
+// end on the main stream, drain end and apply end on the side stream -- printed to stderr.
+struct TraceRec { cudaEvent_t r0, r1, d1, a1; };
+static std::vector<TraceRec> g_trace;
+static bool trace_on() { static const bool on = getenv("BUDDHA_TILE_TRACE") != nullptr; return on; }
+static void trace_dump() {
+  if (g_trace.empty()) return;
+  cudaEvent_t t0 = g_trace[0].r0;
+  for (size_t i = 0; i < g_trace.size(); i++) {
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventSynchronize(g_trace[i].a1);
+    cudaEventElapsedTime(&a, t0, g_trace[i].r0); cudaEventElapsedTime(&b, t0, g_trace[i].r1);
+    cudaEventElapsedTime(&d, t0, g_trace[i].d1); cudaEventElapsedTime(&e, t0, g_trace[i].a1);
+    fprintf(stderr, "launch %2zu: render %.2f..%.2f ms (%.2f)  drain done %.2f (+%.2f)  apply done %.2f (+%.2f)\n",
+            i, a, b, b - a, d, d - b, e, e - d);
+  }
+  for (size_t i = 0; i < g_trace.size(); i++) {
+    cudaEventDestroy(g_trace[i].r0); cudaEventDestroy(g_trace[i].r1);
+    cudaEventDestroy(g_trace[i].d1); cudaEventDestroy(g_trace[i].a1);
+  }
+  g_trace.clear();
+}
+
 // One render launch (+ the orbit drain, + the tile apply when tiling is on) for [first, first+count).
 static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   RenderParams rp = c->rp;
@@ -635,7 +658,7 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       rp.pool = c->d_pool + (size_t)b * (c->pool_entries / 2);
       CU(c, cudaMemsetAsync(rp.tcount, 0, sizeof(uint32_t) * c->n_lists, c->stream));
     }
-    CU(c, cudaMemsetAsync(c->spill[b].count, 0, sizeof(unsigned int) * 2, c->stream));
+    CU(c, cudaMemsetAsync(c->spill[b].count, 0, sizeof(unsigned int) * 4, c->stream));
     uint64_t want = (count + rp.chunk - 1) / rp.chunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
@@ -648,9 +671,16 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     case 2: KERNEL<2><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                   \
     default: KERNEL<3><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); break;                  \
   }
+    TraceRec tr = {};
+    const bool tracing = c->tiled && c->tile_calibrated && trace_on();
+    if (tracing) {
+      cudaEventCreate(&tr.r0); cudaEventCreate(&tr.r1); cudaEventCreate(&tr.d1); cudaEventCreate(&tr.a1);
+      cudaEventRecord(tr.r0, c->stream);
+    }
     BUDDHA_LAUNCH_VARIANT(render_persistent_kernel, grid, kThreadsPerCta, rsmem, c->stream, rp,
                           c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
     CU(c, cudaGetLastError());
+    if (tracing) cudaEventRecord(tr.r1, c->stream);
     // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render
     // kernel of the following launch.
     static const bool serial = getenv("BUDDHA_TILE_SERIAL") != nullptr;  // experiment switch
@@ -662,9 +692,14 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     // orbits the warps could not run with enough lanes: finished with grid-wide refill
     const int dgrid = (grid * kWarpsPerCta + kDrainWarps - 1) / kDrainWarps;
     const size_t ddyn = c->tiled ? (size_t)c->n_tiles * kDrainWarps * sizeof(uint2) : 0;
+    // long leftovers first, one warp per orbit (their z-chain is the critical path of the launch),
+    // then the rest with the lane-group size the volume allows
     BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
-                          c->d_counters, c->spill[b], c->d_spill_next[b]);
-    c->launches += 1;
+                          c->d_counters, c->spill[b], c->d_spill_next[b], 1);
+    BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
+                          c->d_counters, c->spill[b], c->d_spill_next[b] + 1, 0);
+    c->launches += 2;
+    if (tracing) cudaEventRecord(tr.d1, side);
     if (pipelined) {
       // apply this launch's lists while the next launch renders
       CU(c, cudaGetLastError());
@@ -673,6 +708,7 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
         apply_tile_kernel<<<agrid, kApplyWarps * 32, 0, side>>>(
             c->d_hist, rp.tcount, c->d_tcap, c->d_tbase, rp.pool, t, c->tile_warps, c->tile_shift);
       CU(c, cudaEventRecord(c->ev_applied[b], side));
+      if (tracing) { cudaEventRecord(tr.a1, side); g_trace.push_back(tr); }
       c->apply_pending[b] = true;
       c->tile_buf = b ^ 1;
       c->launches += c->n_tiles;
@@ -775,6 +811,7 @@ int buddha_sync(buddha_ctx *c) {
   if (!c) return BUDDHA_EINVAL;
   CU(c, cudaSetDevice(c->params.device));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (trace_on()) trace_dump();
   return BUDDHA_OK;
 }
 
@@ -1153,7 +1190,10 @@ int buddha_merge(buddha_ctx **ctxs, int n, int root) {
                 x->rp.n_seg == r->rp.n_seg;
     for (int k = 0; same && k < x->n_bands; k++) same = x->band_set[k] == r->band_set[k];
     for (int k = 0; same && k < x->rp.n_seg; k++)
-      same = x->rp.seg_start[k] == r->rp.seg_start[k] && x->rp.seg_band[k] == r->rp.seg_band[k];
+      same = x->rp.seg_start[k] == r->rp.seg_start[k] && x->rp.seg_band[k] == r->rp.seg_band[k] &&
+             x->rp.seg_start[k + 1] == r->rp.seg_start[k + 1];
+    same = same && a.max_iterations == b.max_iterations && a.min_iterations == b.min_iterations &&
+           ((a.flags ^ b.flags) & BUDDHA_F_BURNING_SHIP) == 0;
     if (!same) return fail(r, BUDDHA_ESIZE, "context %d differs from the root in canvas or channels", i);
     for (int j = 0; j < i; j++)
       if (ctxs[j]->params.device == x->params.device)

@@ -45,10 +45,10 @@ constexpr int kDeepCap = 63;
 constexpr int kZCap = 87, kZJoint = kZCap - 32;
 constexpr int kCCap = 94;
 constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel with < 32 accepted samples
+constexpr int kDrainLong = 1024;                 // leftovers this long get a warp each, if they are few
 constexpr int kChunk = 4096;                   // granularity of launch sizes (host side)
 constexpr int kMinChunk = 1024, kMaxChunk = 16384;  // sample indices a warp takes per cursor grab
-constexpr int kGenSteps = 2;                   // escape-test steps done by the sampler itself
-constexpr int kT1End = 6;                      // tier 1 covers steps kGenSteps+1 .. kT1End
+constexpr int kT1End = 6;                      // the first exact tier covers steps 1 .. kT1End
 constexpr int kT2End = 22;                     // tier 2 covers steps kT1End+1 .. kT2End
 constexpr int kLateSteps = 24;                 // per-step-tested steps per `late` batch
 constexpr int kBlock = 24;                     // unchecked steps per deep round (= kLateSteps)
@@ -390,7 +390,8 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 // which no later code reads (the `alive` predicate is sticky and NaN compares false).
 
 // Shared-memory work stacks of one warp (structure of arrays: 16-byte accesses, no conflicts).
-//   c_*      t1 (slots 0 up) and t2 (slots kCCap-1 down): candidates that re-compute their state from c
+//   c_*      t0 (slots 0 up): Philox words of candidates the sampler's float pre-test could not
+//            retire; t2 (slots kCCap-1 down): candidates that re-compute their state from c
 //   z_*      late (0 up): it = iterations done; orb (kZCap-1 down): it = steps still to record
 //   deep_*   carry their checkpoint, so suspending a lane does not restart the periodicity search
 //            (long cycles need long uninterrupted windows); meta = (last, age): the age after which
@@ -398,7 +399,7 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 struct WarpQueues {
   double2 deep_c[kDeepCap], deep_z[kDeepCap], deep_r[kDeepCap];
   double2 z_c[kZCap], z_z[kZCap];
-  double2 c_c[kCCap];
+  union { double2 c_c[kCCap]; uint4 c_w[kCCap]; };
   uint2 deep_meta[kDeepCap];
   int z_it[kZCap];
   int pad[(4 - (2 * kDeepCap + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
@@ -409,11 +410,11 @@ static_assert(sizeof(WarpQueues) % 16 == 0, "stack arrays must stay 16-byte alig
 template <bool kDown, int kCap>
 __device__ __forceinline__ int slot_of(int i) { return kDown ? kCap - 1 - i : i; }
 constexpr bool kLate = false, kOrb = true;  // the two stacks in z_*
-constexpr bool kT1 = false, kT2 = true;     // the two stacks in c_*
+constexpr bool kT0 = false, kT2 = true;     // the two stacks in c_*
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
-  int t1_n, t2_n, late_n, deep_n, orb_n;  // stack heights (warp-uniform)
+  int t0_n, t2_n, late_n, deep_n, orb_n;  // stack heights (warp-uniform)
   unsigned long long chunk_base;           // first sample index of the chunk this warp owns
   uint32_t chunk_off, chunk_len;           // progress inside the chunk
   bool exhausted;                          // the global cursor ran past p.end
@@ -578,18 +579,30 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
   }
 }
 
-// (a) sampler + steps 1..kGenSteps (= 2).  One batch = one candidate per lane.  kCommon: max_it >
-// kGenSteps, so both steps count and survivors move on; otherwise the general limit logic runs.
-template <int kVar, bool kCommon>
+// (a) sampler.  One batch = one candidate per lane: Philox, then an FP32 PRE-CLASSIFICATION that
+// retires 82 % of the candidates without a single FP64 instruction (which cost two issue cycles
+// each on this machine, profiles/r02_issue_probes.txt): coordinates from the top 23 bits of the two
+// high Philox words, the cardioid / bulb test and the first two steps in float.  A decision counts
+// only when it clears its threshold by a margin 50 x the largest float error seen over 2^26
+// samples (oracle check: no decided sample disagrees with the reference's FP64 arithmetic):
+//   certainly rejected                      -> counted, done
+//   certainly outside radius 2 after step 1 -> escaped at step 1 (an escaping c is far from the
+//   certainly inside after step 1, outside     cardioid and the bulb, so it was not rejected): too
+//   after step 2                               early for any cutoff >= 2, counted, done
+// Everything else -- samples still inside after two steps and the few undecided ones -- goes to
+// `t0` as its four Philox words; the first exact tier re-derives c from them in FP64.
+constexpr float kPreRejMargin = 0.02f, kPreEscMargin = 0.05f;
+
+template <int kVar>
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
                                           unsigned long long *counters) {
-  static_assert(kGenSteps == 2, "gen_phase is written for two steps");
   const unsigned lane = lane_id();
-  const int allowed = max(0, min(kGenSteps, p.max_it));  // IterateMandelbrot stops at max
-  const bool may_accept = kGenSteps - 1 >= p.min_it;
+  // an escape at step k is "too early" (and inside the limit) for every sample only if
+  // min_it >= k and max_it >= k; otherwise the exact tier has to look at it
+  const bool quick1 = p.min_it >= 1 && p.max_it >= 1, quick2 = p.min_it >= 2 && p.max_it >= 2;
 #pragma unroll 1
-  while (ws.t1_n < 32 && ws.orb_n < 32 && ws.late_n + ws.orb_n <= kZJoint) {
+  while (ws.t0_n < 32) {
     if (ws.chunk_off >= ws.chunk_len) {
       if (ws.exhausted) break;
       // The per-lane counters go to global memory when one of them nears 2^30 (and at the end
@@ -616,31 +629,69 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
     const uint32_t o = ws.chunk_off + lane;
     const bool valid = o < ws.chunk_len;
     ws.chunk_off += 32;
-    uint4 r = philox4x32_10(ws.chunk_base + o, p);
-    const double cx = coord2_from_words(r.x, r.y);
-    const double cy = coord2_from_words(r.z, r.w);
-    const bool rej = (kVar & kVarShip) ? false : rejected2(cx, cy);  // cudabrot.cu:397-399
-    const bool cand = valid && !rej;
-    ws.n_rej += (valid && rej) ? 1u : 0u;
-    double x = cx, y = cy;
-    BUDDHA_ZSTEP(x, y, cx, cy);
-    const bool in1 = cand && !(norm4(x, y) > 16.0);  // still inside after step 1
-    BUDDHA_ZSTEP(x, y, cx, cy);
-    const bool in2 = in1 && !(norm4(x, y) > 16.0);
-    if (kCommon) {
-      ws.steps += cand ? 1u : 0u;
-      ws.steps += in1 ? 1u : 0u;
-      const int slot = slot_of<kT1, kCCap>(push_slot(ws.t1_n, in2));
-      if (in2) q.c_c[slot] = make_double2(cx, cy);
-      if (may_accept) push_orbit<kVar>(p, q, ws, counters, cand && !in2, cx, cy, in1 ? 2 : 1);
-    } else {
-      // max_it <= 2: escapes after the limit do not count; whoever is left has hit max
-      const int cnt = in1 ? 2 : 1;  // steps until the escape (if any)
-      const bool esc = cand && !in2 && cnt <= allowed;
-      ws.steps += cand ? (uint32_t)min(cnt, allowed) : 0u;
-      ws.n_hit += (cand && !esc) ? 1u : 0u;
-      if (may_accept) push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, cnt);
+    const uint4 r = philox4x32_10(ws.chunk_base + o, p);
+    // 2c to ~1e-6: the mantissa trick turns the top 23 bits of a word into [1, 2)
+    const float cx = __fmaf_rn(__uint_as_float(0x3F800000u | (r.y >> 9)), 8.0f, -12.0f);
+    const float cy = __fmaf_rn(__uint_as_float(0x3F800000u | (r.w >> 9)), 8.0f, -12.0f);
+    const float i2 = cy * cy;
+    bool rej = false;
+    if constexpr ((kVar & kVarShip) == 0) {  // rejected2 in float (cudabrot.cu:284-298, :397-399)
+      const float q0 = cx - 0.5f, qq = __fmaf_rn(q0, q0, i2), sx = __fmaf_rn(q0, 2.0f, qq);
+      const float t = cx + 2.0f;
+      rej = (qq * sx < i2 - kPreRejMargin) || (__fmaf_rn(t, t, i2) < 0.25f - kPreRejMargin);
     }
+    const float x1 = __fmaf_rn(__fmaf_rn(cx, cx, -i2), 0.5f, cx);
+    const float y1 = (kVar & kVarShip) ? __fmaf_rn(fabsf(cx), fabsf(cy), cy) : __fmaf_rn(cx, cy, cy);
+    const float n1 = __fmaf_rn(y1, y1, x1 * x1);
+    const float x2 = __fmaf_rn(__fmaf_rn(x1, x1, -y1 * y1), 0.5f, cx);
+    const float y2 = (kVar & kVarShip) ? __fmaf_rn(fabsf(x1), fabsf(y1), cy) : __fmaf_rn(x1, y1, cy);
+    const float n2 = __fmaf_rn(y2, y2, x2 * x2);
+    const bool esc1 = quick1 && !rej && n1 > 16.0f + kPreEscMargin;
+    const bool esc2 = quick2 && !rej && n1 < 16.0f - kPreEscMargin && n2 > 16.0f + kPreEscMargin;
+    ws.n_rej += (valid && rej) ? 1u : 0u;
+    ws.steps += (valid && esc1) ? 1u : 0u;
+    ws.steps += (valid && esc2) ? 2u : 0u;
+    const bool keep = valid && !(rej || esc1 || esc2);
+    const int slot = slot_of<kT0, kCCap>(push_slot(ws.t0_n, keep));
+    if (keep) q.c_w[slot] = r;
+  }
+  __syncwarp();
+}
+
+// (b0) the first exact tier: pops up to 32 candidates the sampler could not retire, derives c from
+// their Philox words in FP64, applies the exact cardioid / bulb test and runs steps 1..kT1End with
+// the exact per-step test.  Survivors go to t2 as c only.
+template <int kVar>
+__device__ __forceinline__ void first_tier_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                                 unsigned long long *counters) {
+  const int take = min(ws.t0_n, 32);
+  const bool act = (int)lane_id() < take;
+  ws.t0_n -= take;
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  if (act) r = q.c_w[slot_of<kT0, kCCap>(ws.t0_n + (int)lane_id())];
+  const double cx = coord2_from_words(r.x, r.y);
+  const double cy = coord2_from_words(r.z, r.w);
+  const bool rej = (kVar & kVarShip) ? false : rejected2(cx, cy);  // cudabrot.cu:397-399
+  ws.n_rej += (act && rej) ? 1u : 0u;
+  const bool cand = act && !rej;
+  double x = cx, y = cy;
+  bool alive = cand;
+  int cnt = 0;
+  tested_steps<kVar, kT1End>(x, y, cx, cy, alive, cnt);
+  if (p.max_it > kT1End) {
+    // the common case: every step counts, survivors move on
+    ws.steps += (uint32_t)cnt;
+    const int slot = slot_of<kT2, kCCap>(push_slot(ws.t2_n, alive));
+    if (alive) q.c_c[slot] = make_double2(cx, cy);
+    if (kT1End - 1 >= p.min_it) push_orbit<kVar>(p, q, ws, counters, cand && !alive, cx, cy, cnt);
+  } else {
+    // max_it falls inside this tier (or is 0): escapes after the limit do not count, the rest
+    // has hit max (IterateMandelbrot stops at max, cudabrot.cu:326)
+    const int allowed = max(p.max_it, 0);
+    const bool esc = cand && !alive && cnt <= allowed;
+    ws.steps += cand ? (uint32_t)min(cnt, allowed) : 0u;
+    ws.n_hit += (cand && !esc) ? 1u : 0u;
+    if (kT1End - 1 >= p.min_it) push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, cnt);
   }
   __syncwarp();
 }
@@ -668,7 +719,7 @@ __device__ __forceinline__ void tier_phase(const RenderParams &p, WarpQueues &q,
   const bool act = (int)lane_id() < take;
   src_n -= take;
   double2 c = make_double2(0.0, 0.0);
-  if (act) c = q.c_c[slot_of<kToLate ? kT2 : kT1, kCCap>(src_n + (int)lane_id())];
+  if (act) c = q.c_c[slot_of<kT2, kCCap>(src_n + (int)lane_id())];
   const double cx = c.x, cy = c.y;
   double x = cx, y = cy;
 #pragma unroll
@@ -954,15 +1005,19 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
 struct OrbitSpill {
   double4 *entries;          // (cx, cy, x, y)
   int *steps;                // remaining steps
-  unsigned int *count;       // entries written
+  unsigned int *count;       // [0] entries written, [1] / [2] cursors of the two drain passes,
+                             // [3] entries with at least kDrainLong steps left
   unsigned int capacity;
 };
 
 // Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles list entries per warp.
 constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 
+#ifndef BUDDHA_RENDER_MAXREG
+#define BUDDHA_RENDER_MAXREG 72
+#endif
 template <int kVar>
-__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSm)
+__global__ void __maxnreg__(BUDDHA_RENDER_MAXREG)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
                          unsigned long long *__restrict__ counters, OrbitSpill spill) {
@@ -973,7 +1028,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                      blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
   tile_counters_load(p, sink, true);
   WarpState ws;
-  ws.t1_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
+  ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
   ws.chunk_base = 0;
   ws.chunk_off = ws.chunk_len = 0;
   ws.exhausted = false;
@@ -989,7 +1044,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     // to holds < 32 entries.  Once the sample range is used up (`dry`) the partial stacks are run
     // dry, upstream first.
     const bool dry = ws.exhausted && ws.chunk_off >= ws.chunk_len;
-    const bool dry1 = dry && ws.t1_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
+    const bool dry1 = dry && ws.t0_n == 0, dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
     if (ws.orb_n >= 32 || (ws.orb_n >= kOrbExit && ws.late_n + ws.orb_n > kZJoint)) {
       orbit_phase<kVar>(p, q, ws, sink);
     } else if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint || (dry2 && ws.late_n > 0)) {
@@ -998,11 +1053,10 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
       deep_phase<kVar>(p, q, ws, dry3, counters);
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
       tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, ws.t2_n, counters);
-    } else if (ws.t1_n >= 32 || (dry && ws.t1_n > 0)) {
-      tier_phase<kVar, kGenSteps, kT1End - kGenSteps, false>(p, q, ws, ws.t1_n, counters);
+    } else if (ws.t0_n >= 32 || (dry && ws.t0_n > 0)) {
+      first_tier_phase<kVar>(p, q, ws, counters);
     } else if (!dry) {
-      if (p.max_it > kGenSteps) gen_phase<kVar, true>(p, q, ws, cursor, counters);
-      else gen_phase<kVar, false>(p, q, ws, cursor, counters);
+      gen_phase<kVar>(p, q, ws, cursor, counters);
     } else {
       break;
     }
@@ -1012,14 +1066,17 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     unsigned base = 0;
     if (lane_id() == 0) base = atomicAdd(spill.count, (unsigned)ws.orb_n);
     base = __shfl_sync(kFull, base, 0);
-    for (int k = lane_id(); k < ws.orb_n; k += 32) {
-      unsigned dst = base + k;
-      if (dst < spill.capacity) {
-        const int slot = slot_of<kOrb, kZCap>(k);
-        spill.entries[dst] = make_double4(q.z_c[slot].x, q.z_c[slot].y, q.z_z[slot].x, q.z_z[slot].y);
-        spill.steps[dst] = q.z_it[slot];
-      }
+    const int k = (int)lane_id();   // orb_n < 32 here
+    bool is_long = false;
+    if (k < ws.orb_n && base + k < spill.capacity) {
+      const int slot = slot_of<kOrb, kZCap>(k);
+      const int n = q.z_it[slot];
+      spill.entries[base + k] = make_double4(q.z_c[slot].x, q.z_c[slot].y, q.z_z[slot].x, q.z_z[slot].y);
+      spill.steps[base + k] = n;
+      is_long = ((kVar & kVarFused) ? (n & ((1 << kOrbStepBits) - 1)) : n) >= kDrainLong;
     }
+    const unsigned nl = __popc(__ballot_sync(kFull, is_long));
+    if (lane_id() == 0 && nl) atomicAdd(spill.count + 3, nl);
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
@@ -1042,7 +1099,7 @@ template <int kVar>
 __global__ void __launch_bounds__(kDrainWarps * 32)
 orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
                    unsigned long long *__restrict__ counters, OrbitSpill spill,
-                   unsigned int *__restrict__ next) {
+                   unsigned int *__restrict__ next, int long_pass) {
   const unsigned total = min(*spill.count, spill.capacity);
   extern __shared__ uint2 tile_tab[];
   const uint32_t gwarp = blockIdx.x * kDrainWarps + (threadIdx.x >> 5);
@@ -1056,11 +1113,22 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
+  // Two passes per launch.  The leftovers are mostly short, but one 20000-step orbit stepped by a
+  // small lane group would keep the whole launch waiting (3.7 ms at g = 1), so when the LONG
+  // entries (>= kDrainLong steps) are few enough to get a warp each, the first pass (long_pass)
+  // finishes them with g = 32 and the second takes the rest; otherwise the first pass does nothing
+  // and the second takes everything with the group size the volume allows.
   int g = 32;
-  {
-    unsigned long long warps = (unsigned long long)gridDim.x * kDrainWarps;
-    if (p.tile_shift && warps > p.n_warps) warps = p.n_warps;
-    const unsigned long long lanes = 2ull * 32ull * warps;
+  unsigned long long warps = (unsigned long long)gridDim.x * kDrainWarps;
+  if (p.tile_shift && warps > p.n_warps) warps = p.n_warps;
+  const unsigned long long lanes = 2ull * 32ull * warps;
+  const bool split = (unsigned long long)spill.count[3] * 32ull <= lanes;
+  int steps_lo = 0, steps_hi = 0x7fffffff;
+  if (long_pass) {
+    if (!split) return;
+    steps_lo = kDrainLong;
+  } else {
+    if (split) steps_hi = kDrainLong;
     while (g > 1 && (unsigned long long)total * g > lanes) g >>= 1;
   }
   const int lane = (int)lane_id();
@@ -1083,12 +1151,16 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
           const double4 e = spill.entries[idx];
           cx = e.x; cy = e.y; x = e.z; y = e.w; n = spill.steps[idx];
           if constexpr ((kVar & kVarFused) != 0) { mask = (unsigned)n >> kOrbStepBits; n &= (1 << kOrbStepBits) - 1; }
+          if (n < steps_lo || n >= steps_hi) n = 0;   // the other pass's entry
         } else {
           more = false;
         }
       }
     }
-    if (__ballot_sync(kFull, n > 0) == 0u) break;
+    if (__ballot_sync(kFull, n > 0) == 0u) {
+      if (__ballot_sync(kFull, more) == 0u) break;
+      continue;  // only entries of the other pass so far: grab again
+    }
     OrbitLane o = {sub < n, cx, cy, 0.0, 0.0, (int)(mask << kOrbStepBits) | 1, 0u};
 #pragma unroll 1
     for (int k = 0; k < g; k++) {

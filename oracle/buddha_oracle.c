@@ -537,3 +537,61 @@ uint64_t oracle_check_period3(uint64_t seed, uint64_t first, uint64_t count, int
   if (inset) *inset = in;
   return bad;
 }
+
+/* The sampler's FP32 pre-classification (buddha_kernels.cuh: prefilter), restated: coordinates from
+ * the top 23 bits of the two high Philox words, cardioid / bulb and the first two steps in float,
+ * each decision only when it clears its threshold by a margin.  0 = undecided (goes on to the exact
+ * FP64 path), 1 = certainly rejected, 2 = certainly escapes at step 1, 3 = certainly at step 2. */
+int oracle_prefilter_class(uint32_t hi_re, uint32_t hi_im, int ship, float m_rej, float m_esc) {
+  union { uint32_t u; float f; } a, b;
+  a.u = 0x3F800000u | (hi_re >> 9);
+  b.u = 0x3F800000u | (hi_im >> 9);
+  const float cx = fmaf(a.f, 8.0f, -12.0f), cy = fmaf(b.f, 8.0f, -12.0f);   /* 2 * c */
+  const float i2 = cy * cy;
+  if (!ship) {
+    const float q0 = cx - 0.5f, q = fmaf(q0, q0, i2), s = fmaf(q0, 2.0f, q), lhs = q * s;
+    const float t = cx + 2.0f, bb = fmaf(t, t, i2);
+    if (lhs < i2 - m_rej || bb < 0.25f - m_rej) return 1;
+  }
+  const float x1 = fmaf(fmaf(cx, cx, -i2), 0.5f, cx);
+  const float y1 = ship ? fmaf(fabsf(cx), fabsf(cy), cy) : fmaf(cx, cy, cy);
+  const float n1 = fmaf(y1, y1, x1 * x1);
+  if (n1 > 16.0f + m_esc) return 2;
+  if (!(n1 < 16.0f - m_esc)) return 0;
+  const float a2 = y1 * y1;
+  const float x2 = fmaf(fmaf(x1, x1, -a2), 0.5f, cx);
+  const float y2 = ship ? fmaf(fabsf(x1), fabsf(y1), cy) : fmaf(x1, y1, cy);
+  const float n2 = fmaf(y2, y2, x2 * x2);
+  if (n2 > 16.0f + m_esc) return 3;
+  return 0;
+}
+
+/* Evidence for the pre-classification: every decided sample must agree with the reference's own
+ * arithmetic (rejected <=> oracle_rejected; "escapes at step k" <=> not rejected and
+ * IterateMandelbrot returns k-1).  Returns the number of disagreements (must be 0); counts[4] =
+ * samples per class. */
+uint64_t oracle_check_prefilter(uint64_t seed, uint64_t first, uint64_t count, int ship,
+                                float m_rej, float m_esc, uint64_t counts[4]) {
+  uint64_t bad = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : bad, c0, c1, c2, c3)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    const uint64_t s = first + k;
+    uint32_t ctr[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0u, 0u};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t o[4];
+    oracle_philox4x32_10(ctr, key, o);
+    const int cls = oracle_prefilter_class(o[1], o[3], ship, m_rej, m_esc);
+    if (cls == 0) { c0++; continue; }
+    const double cre = uniform_to_coord(o[0], o[1]), cim = uniform_to_coord(o[2], o[3]);
+    const int rej = ship ? 0 : oracle_rejected(cre, cim);
+    if (cls == 1) { c1++; if (!rej) bad++; continue; }
+    const int it = ship ? oracle_escape_iterations_ship(cre, cim, 3)
+                        : oracle_escape_iterations(cre, cim, 3);
+    if (cls == 2) { c2++; if (rej || it != 0) bad++; }
+    else { c3++; if (rej || it != 1) bad++; }
+  }
+  if (counts) { counts[0] = c0; counts[1] = c1; counts[2] = c2; counts[3] = c3; }
+  return bad;
+}

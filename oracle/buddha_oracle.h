@@ -134,6 +134,13 @@ int oracle_period3_flag(double c_real, double c_imag, float limit);
 uint64_t oracle_check_period3(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
                               float limit, uint64_t *flagged, uint64_t *inset);
 
+/* The sampler's FP32 pre-classification restated (0 undecided, 1 rejected, 2 / 3 escapes at step
+ * 1 / 2), and the check that every decided sample agrees with the reference's arithmetic (returns
+ * the disagreements: must be 0; counts[4] = samples per class). */
+int oracle_prefilter_class(uint32_t hi_re, uint32_t hi_im, int ship, float m_rej, float m_esc);
+uint64_t oracle_check_prefilter(uint64_t seed, uint64_t first, uint64_t count, int ship,
+                                float m_rej, float m_esc, uint64_t counts[4]);
+
 #ifdef __cplusplus
 }
 #endif

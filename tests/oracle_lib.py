@@ -202,6 +202,19 @@ def check_period3(seed, first, count, max_iter, limit=0.96):
     return int(bad), fl.value, ins.value
 
 
+def check_prefilter(seed, first, count, ship=False, m_rej=0.02, m_esc=0.05):
+    """(decided samples that disagree with the reference's arithmetic -- must be 0, [undecided,
+    rejected, escapes at step 1, at step 2]): the evidence behind the sampler's FP32
+    pre-classification (buddha_kernels.cuh: gen_phase)."""
+    L = lib()
+    L.oracle_check_prefilter.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_float,
+                                         C.c_float, C.POINTER(C.c_uint64)]
+    L.oracle_check_prefilter.restype = C.c_uint64
+    cnt = (C.c_uint64 * 4)()
+    bad = L.oracle_check_prefilter(seed, first, count, int(ship), m_rej, m_esc, cnt)
+    return int(bad), [int(x) for x in cnt]
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

@@ -203,3 +203,17 @@ def test_period3_component_test_is_conservative(oracle):
         assert 0.35 < flagged / inset < 0.46          # period-3 components: ~42 % of what is left
     bad, _, _ = oracle.check_period3(1337, 0, 1 << 22, 20000, limit=1.05)
     assert bad > 0
+
+
+def test_sampler_prefilter_is_conservative(oracle):
+    """The sampler retires candidates on an FP32 pre-classification (rejected / escapes at step 1 /
+    at step 2) when the float value clears its threshold by a margin.  With the kernel's margins no
+    decided sample may disagree with the reference's FP64 arithmetic (cudabrot.cu:284-298,
+    :319-340); with the margins at zero the float error must show up, i.e. the check can fail."""
+    for ship in (False, True):
+        for seed, first in ((1337, 0), (7, 1 << 44)):
+            bad, cnt = oracle.check_prefilter(seed, first, 1 << 24, ship=ship)
+            assert bad == 0
+            assert 0.15 < cnt[0] / (1 << 24) < 0.30         # what still needs the exact path
+    bad, _ = oracle.check_prefilter(1337, 0, 1 << 26, m_rej=0.0, m_esc=0.0)
+    assert bad > 0
