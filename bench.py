@@ -53,6 +53,15 @@ WORKLOADS = {
     "cfg5_4k_a": (4000, 4000, 100, 20, FULL, 1 << 32),
     "cfg5_4k_b": (4000, 4000, 1000, 20, FULL, 1 << 32),
     "cfg5_4k_c": (4000, 4000, 20000, 20, FULL, 1 << 32),
+    # dense canvases: every orbit point lands in a few cells (hot-address reductions); the question
+    # north_star (d) raises -- would shared-memory privatised tiles pay? -- is answered by whether
+    # the rate drops as the canvas shrinks (profiles/r02_dense_canvas.txt)
+    "dense64": (64, 64, 1000, 20, FULL, 1 << 32),
+    "dense256": (256, 256, 1000, 20, FULL, 1 << 32),
+    "dense1k": (1000, 1000, 1000, 20, FULL, 1 << 32),
+    "dense4k": (4000, 4000, 1000, 20, FULL, 1 << 32),
+    # a zoom that keeps most of the orbit points: the 2000x2000 window around the main body
+    "zoom_dense": (2000, 2000, 1000, 20, (-1.6, 0.6, -1.1, 1.1), 1 << 32),
 }
 # fused multi-channel workloads: [(max-iter, min-cutoff)] per channel (BASELINE.json configs[4])
 CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)],

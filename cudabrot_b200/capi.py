@@ -32,7 +32,7 @@ EXPORTS = [
     "buddha_probe_red_peak", "buddha_read_channel", "buddha_tonemap_channel_u16",
     "buddha_get_channel_counters", "buddha_device_histogram_cells",
     "buddha_add_histogram_async", "buddha_snapshot", "buddha_read_snapshot",
-    "buddha_tonemap_snapshot_u16", "buddha_histogram_digest",
+    "buddha_tonemap_snapshot_u16", "buddha_histogram_digest", "buddha_combine_rgb_u16",
 ]
 MAX_CHANNELS = 4
 
@@ -136,6 +136,8 @@ def lib():
     L.buddha_tonemap_snapshot_u16.argtypes = [ctx, C.c_int, C.c_double, C.c_int, C.c_void_p,
                                               C.c_size_t, u32p, dblp]
     L.buddha_histogram_digest.argtypes = [ctx, C.c_int, u64p]
+    L.buddha_combine_rgb_u16.argtypes = [ctx, C.POINTER(C.c_int), C.c_double, C.c_int, C.c_double,
+                                         C.c_int, C.c_void_p, C.c_size_t, u32p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("buddha_abi_version",):

@@ -11,6 +11,8 @@
 //   BUDDHA_TILE_LAUNCH_LOG2   log2 of the largest launch of the tiled pipeline (30)
 //   BUDDHA_TILE_SERIAL        apply / drain on the render stream (needed under ncu kernel replay)
 //   BUDDHA_PAD_SMEM           extra dynamic shared memory per CTA (occupancy experiments)
+//   BUDDHA_NO_CARRY           drain the leftover orbits after every pipeline launch (no carry-over)
+//   BUDDHA_TILE_TRACE         print device timestamps of every pipeline launch to stderr
 #include "../../include/buddha.h"
 #include "buddha_kernels.cuh"
 
@@ -91,6 +93,7 @@ struct buddha_ctx {
   uint32_t *d_snap;               // snapshot of the device histogram (all bands)
   uint32_t *d_snap_preload;       // fused: snapshot of the loaded counts
   bool snap_valid;
+  uint16_t *d_planes;             // colour combine: three grey planes + the RGB image
   unsigned long long *d_digest;   // block digests (buddha_histogram_digest)
   size_t digest_capacity;
   RenderParams rp;
@@ -377,11 +380,25 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   c->render_smem = kQueueBytes;
   if (const char *e = getenv("BUDDHA_PAD_SMEM")) c->smem_pad = (size_t)atoi(e);  // occupancy experiments
   c->variant = ((p->flags & BUDDHA_F_BURNING_SHIP) ? kVarShip : 0) | (n_ch > 1 ? kVarFused : 0);
-  const void *render_fns[4] = {(const void *)render_persistent_kernel<0>,
-                               (const void *)render_persistent_kernel<1>,
-                               (const void *)render_persistent_kernel<2>,
-                               (const void *)render_persistent_kernel<3>};
-  const void *render_fn = render_fns[c->variant];
+  // tiled contexts (decided from the size of the device histogram) take the lean-register build
+  {
+    const char *e;
+    size_t min_mb = 640;
+    if ((e = getenv("BUDDHA_TILE_MIN_MB"))) min_mb = (size_t)strtoull(e, nullptr, 10);
+    const size_t bands = n_ch > 1 ? (size_t)c->n_bands : 1;
+    c->tiled = !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
+               ((p->flags & BUDDHA_F_FORCE_TILED) != 0 ||
+                c->ch_cells * bands * sizeof(uint32_t) >= (min_mb << 20));
+  }
+  const void *render_fns[8] = {(const void *)render_persistent_kernel<0, kRegsWide>,
+                               (const void *)render_persistent_kernel<1, kRegsWide>,
+                               (const void *)render_persistent_kernel<2, kRegsWide>,
+                               (const void *)render_persistent_kernel<3, kRegsWide>,
+                               (const void *)render_persistent_kernel<0, kRegsLean>,
+                               (const void *)render_persistent_kernel<1, kRegsLean>,
+                               (const void *)render_persistent_kernel<2, kRegsLean>,
+                               (const void *)render_persistent_kernel<3, kRegsLean>};
+  const void *render_fn = render_fns[c->variant + (c->tiled ? 4 : 0)];
   cudaFuncAttributes fattr;
   cudaError_t st = cudaFuncGetAttributes(&fattr, render_fn);
   if (st == cudaSuccess)
@@ -429,11 +446,7 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   {
     // tile-binned scatter: on for histograms >= 640 MB (config 3: 1.6 GB; crossover measured with tools/gpu_threshold.py), or when forced (tests)
     const char *e;
-    size_t min_mb = 640;
-    if ((e = getenv("BUDDHA_TILE_MIN_MB"))) min_mb = (size_t)strtoull(e, nullptr, 10);
     const bool forced = (p->flags & BUDDHA_F_FORCE_TILED) != 0;
-    c->tiled = !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
-               (forced || c->dev_cells * sizeof(uint32_t) >= (min_mb << 20));
     if (c->tiled) {
       c->tile_shift = forced ? 12 : 24;  // 16 KB test tiles / 64 MB production tiles
       if ((e = getenv("BUDDHA_TILE_SHIFT"))) c->tile_shift = atoi(e);
@@ -470,6 +483,16 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       CUC(cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->ev_applied[0], cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->ev_applied[1], cudaEventDisableTiming));
+      {
+        double4 *ce = nullptr; int *cs = nullptr; unsigned int *cc = nullptr;
+        CUC(cudaMalloc(&ce, sizeof(double4) * (size_t)c->tile_warps * 32));
+        CUC(cudaMalloc(&cs, sizeof(int) * (size_t)c->tile_warps * 32));
+        CUC(cudaMalloc(&cc, sizeof(unsigned int) * c->tile_warps));
+        CUC(cudaMemsetAsync(cc, 0, sizeof(unsigned int) * c->tile_warps, c->stream));
+        for (int k = 0; k < 2; k++) {
+          c->spill[k].carry_entries = ce; c->spill[k].carry_steps = cs; c->spill[k].carry_count = cc;
+        }
+      }
       CUC(cudaMalloc(&c->d_tcap, sizeof(uint32_t) * c->n_tiles));
       CUC(cudaMalloc(&c->d_tbase, sizeof(uint32_t) * c->n_tiles));
       CUC(cudaMemsetAsync(c->d_tcap, 0, sizeof(uint32_t) * c->n_tiles, c->stream));
@@ -495,6 +518,8 @@ void buddha_destroy(buddha_ctx *c) {
   for (int b = 0; b < 2; b++) {
     cudaFree(c->spill[b].entries); cudaFree(c->spill[b].steps); cudaFree(c->spill[b].count);
   }
+  cudaFree(c->spill[0].carry_entries); cudaFree(c->spill[0].carry_steps);
+  cudaFree(c->spill[0].carry_count);
   if (c->apply_stream) { cudaStreamSynchronize(c->apply_stream); cudaStreamDestroy(c->apply_stream); }
   if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
   if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
@@ -510,6 +535,7 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->ev_added) cudaEventDestroy(c->ev_added);
   if (c->ev_snap) cudaEventDestroy(c->ev_snap);
   cudaFree(c->d_stage); cudaFree(c->d_snap); cudaFree(c->d_snap_preload); cudaFree(c->d_digest);
+  cudaFree(c->d_planes);
   cudaFree(c->d_preload);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -630,7 +656,8 @@ static void trace_dump() {
 }
 
 // One render launch (+ the orbit drain, + the tile apply when tiling is on) for [first, first+count).
-static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
+static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count, bool carry_in = false,
+                         bool carry_out = false) {
   RenderParams rp = c->rp;
   rp.end = first + count;
   if (c->params.flags & BUDDHA_F_SIMPLE_KERNEL) {
@@ -662,6 +689,11 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     uint64_t want = (count + rp.chunk - 1) / rp.chunk;  // warps that can get work at all
     uint64_t ctas = (want + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = (int)std::min<uint64_t>(ctas, (uint64_t)c->grid);
+    if (carry_in || carry_out) grid = c->grid;  // the same warps must exist in both launches
+    for (int k = 0; k < 2; k++) {
+      c->spill[k].carry_in = carry_in ? 1 : 0;
+      c->spill[k].carry_out = carry_out ? 1 : 0;
+    }
     const size_t dyn = c->tiled ? c->tile_smem : 0;
     const size_t rsmem = c->render_smem + c->smem_pad + dyn;
 #define BUDDHA_LAUNCH_VARIANT(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                         \
@@ -677,8 +709,18 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
       cudaEventCreate(&tr.r0); cudaEventCreate(&tr.r1); cudaEventCreate(&tr.d1); cudaEventCreate(&tr.a1);
       cudaEventRecord(tr.r0, c->stream);
     }
-    BUDDHA_LAUNCH_VARIANT(render_persistent_kernel, grid, kThreadsPerCta, rsmem, c->stream, rp,
-                          c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
+#define BUDDHA_LAUNCH_RENDER(REGS)                                                          \
+  switch (c->variant) {                                                                     \
+    case 0: render_persistent_kernel<0, REGS><<<grid, kThreadsPerCta, rsmem, c->stream>>>(  \
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]); break;                     \
+    case 1: render_persistent_kernel<1, REGS><<<grid, kThreadsPerCta, rsmem, c->stream>>>(  \
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]); break;                     \
+    case 2: render_persistent_kernel<2, REGS><<<grid, kThreadsPerCta, rsmem, c->stream>>>(  \
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]); break;                     \
+    default: render_persistent_kernel<3, REGS><<<grid, kThreadsPerCta, rsmem, c->stream>>>( \
+        rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]); break;                     \
+  }
+    if (c->tiled) { BUDDHA_LAUNCH_RENDER(kRegsLean) } else { BUDDHA_LAUNCH_RENDER(kRegsWide) }
     CU(c, cudaGetLastError());
     if (tracing) cudaEventRecord(tr.r1, c->stream);
     // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render
@@ -693,12 +735,15 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count) {
     const int dgrid = (grid * kWarpsPerCta + kDrainWarps - 1) / kDrainWarps;
     const size_t ddyn = c->tiled ? (size_t)c->n_tiles * kDrainWarps * sizeof(uint2) : 0;
     // long leftovers first, one warp per orbit (their z-chain is the critical path of the launch),
-    // then the rest with the lane-group size the volume allows
-    BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
-                          c->d_counters, c->spill[b], c->d_spill_next[b], 1);
-    BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
-                          c->d_counters, c->spill[b], c->d_spill_next[b] + 1, 0);
-    c->launches += 2;
+    // then the rest with the lane-group size the volume allows; nothing to drain when the
+    // leftovers were carried over to the next launch
+    if (!carry_out) {
+      BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
+                            c->d_counters, c->spill[b], c->d_spill_next[b], 1);
+      BUDDHA_LAUNCH_VARIANT(orbit_drain_kernel, dgrid, kDrainWarps * 32, ddyn, side, rp, c->d_hist,
+                            c->d_counters, c->spill[b], c->d_spill_next[b] + 1, 0);
+      c->launches += 2;
+    }
     if (tracing) cudaEventRecord(tr.d1, side);
     if (pipelined) {
       // apply this launch's lists while the next launch renders
@@ -780,10 +825,14 @@ static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   if (const char *e = getenv("BUDDHA_TILE_LAUNCH_LOG2")) max_launch = ldexp(1.0, atoi(e));
   uint64_t max_n = (uint64_t)std::min(std::max(per, 65536.0), max_launch);
   max_n = std::max<uint64_t>(max_n / kChunk * kChunk, kChunk);
+  bool carried = false;
   while (count > 0) {
     uint64_t n = std::min(count, max_n);
-    int rc = launch_render(c, first, n);
+    static const bool no_carry = getenv("BUDDHA_NO_CARRY") != nullptr;  // experiment switch
+    const bool more = count > n && !no_carry;  // leftovers ride along to the next launch of this call
+    int rc = launch_render(c, first, n, carried, more);
     if (rc) return rc;
+    carried = more;
     first += n;
     count -= n;
   }
@@ -946,7 +995,9 @@ int buddha_tonemap_u16(buddha_ctx *c, double gamma, int big_endian, uint16_t *ho
 }
 
 static int tonemap_impl(buddha_ctx *c, int slot, int channel, double gamma, int big_endian,
-                        uint16_t *host_out, size_t cells, uint32_t *max_out, double *scale_out) {
+                        uint16_t *host_out, size_t cells, uint32_t *max_out, double *scale_out,
+                        uint16_t *dev_out = nullptr) {
+  // dev_out: leave the image in this device buffer instead of copying it to the host
   if (!c) return BUDDHA_EINVAL;
   if (channel < 0 || channel >= c->n_ch) return fail(c, BUDDHA_EINVAL, "no channel %d", channel);
   if (host_out && cells != c->ch_cells)
@@ -972,7 +1023,7 @@ static int tonemap_impl(buddha_ctx *c, int slot, int channel, double gamma, int 
   double scale = ((double)0xffff) / ((double)mx);  // :436 (inf when the histogram is empty)
   if (max_out) *max_out = mx;
   if (scale_out) *scale_out = scale;
-  if (!host_out) {
+  if (!host_out && !dev_out) {
     if (slot == 0) {
       CU(c, cudaEventRecord(c->ev_tb, st));
       c->tonemap_timed = true;
@@ -1027,10 +1078,11 @@ static int tonemap_impl(buddha_ctx *c, int slot, int channel, double gamma, int 
     CU(c, cudaMemcpyAsync(tb.d_thr, thr.data(), sizeof(uint32_t) * 65536, cudaMemcpyHostToDevice,
                           st));
   }
-  if (!tb.d_gray) CU(c, cudaMalloc(&tb.d_gray, sizeof(uint16_t) * c->ch_cells));
+  if (!dev_out && !tb.d_gray) CU(c, cudaMalloc(&tb.d_gray, sizeof(uint16_t) * c->ch_cells));
+  uint16_t *d_img = dev_out ? dev_out : tb.d_gray;
 
   // pass 2: the map itself, 4 B read + 2 B written per pixel
-  tonemap_kernel<<<blocks, 256, 0, st>>>(d_src, tb.d_gray, c->ch_cells, tb.d_lut, lut_size,
+  tonemap_kernel<<<blocks, 256, 0, st>>>(d_src, d_img, c->ch_cells, tb.d_lut, lut_size,
                                          tb.d_thr, big_endian ? 1 : 0);
   CU(c, cudaGetLastError());
   c->launches += 1;
@@ -1038,8 +1090,9 @@ static int tonemap_impl(buddha_ctx *c, int slot, int channel, double gamma, int 
     CU(c, cudaEventRecord(c->ev_tb, st));
     c->tonemap_timed = true;
   }
-  CU(c, cudaMemcpyAsync(host_out, tb.d_gray, sizeof(uint16_t) * c->ch_cells, cudaMemcpyDeviceToHost,
-                        st));
+  if (host_out)
+    CU(c, cudaMemcpyAsync(host_out, d_img, sizeof(uint16_t) * c->ch_cells, cudaMemcpyDeviceToHost,
+                          st));
   CU(c, cudaStreamSynchronize(st));  // (lut / thr are host vectors read by the copies above)
   return BUDDHA_OK;
 }
@@ -1048,6 +1101,35 @@ int buddha_tonemap_channel_u16(buddha_ctx *c, int channel, double gamma, int big
                                uint16_t *host_out, size_t cells, uint32_t *max_out,
                                double *scale_out) {
   return tonemap_impl(c, 0, channel, gamma, big_endian, host_out, cells, max_out, scale_out);
+}
+
+int buddha_combine_rgb_u16(buddha_ctx *c, const int channels[3], double gamma, int mode,
+                           double hue_adjust, int big_endian, uint16_t *host_rgb, size_t pixels,
+                           uint32_t max_out[3]) {
+  if (!c || !channels || !host_rgb) return BUDDHA_EINVAL;
+  if (pixels != c->ch_cells)
+    return fail(c, BUDDHA_ESIZE, "image buffer has %zu pixels, canvas has %zu", pixels, c->ch_cells);
+  if (mode != BUDDHA_COMBINE_RGB && mode != BUDDHA_COMBINE_HSL)
+    return fail(c, BUDDHA_EINVAL, "unknown combine mode %d", mode);
+  CU(c, cudaSetDevice(c->params.device));
+  if (!c->d_planes) CU(c, cudaMalloc(&c->d_planes, sizeof(uint16_t) * c->ch_cells * 6));
+  for (int k = 0; k < 3; k++) {
+    uint32_t mx = 0;
+    int rc = tonemap_impl(c, 0, channels[k], gamma, 0, nullptr, 0, &mx, nullptr,
+                          c->d_planes + (size_t)k * c->ch_cells);
+    if (rc) return rc;
+    if (max_out) max_out[k] = mx;
+  }
+  uint16_t *d_rgb = c->d_planes + 3 * c->ch_cells;
+  combine_rgb_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
+      c->d_planes, c->d_planes + c->ch_cells, c->d_planes + 2 * c->ch_cells, d_rgb, c->ch_cells, mode,
+      hue_adjust, big_endian ? 1 : 0);
+  CU(c, cudaGetLastError());
+  c->launches += 1;
+  CU(c, cudaMemcpyAsync(host_rgb, d_rgb, sizeof(uint16_t) * 3 * c->ch_cells, cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return BUDDHA_OK;
 }
 
 // ---- asynchronous host transfers ------------------------------------------------------------

@@ -584,7 +584,7 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
 // each on this machine, profiles/r02_issue_probes.txt): coordinates from the top 23 bits of the two
 // high Philox words, the cardioid / bulb test and the first two steps in float.  A decision counts
 // only when it clears its threshold by a margin 50 x the largest float error seen over 2^26
-// samples (oracle check: no decided sample disagrees with the reference's FP64 arithmetic):
+// samples (CPU check in the test suite: no decided sample disagrees with the reference FP64 arithmetic):
 //   certainly rejected                      -> counted, done
 //   certainly outside radius 2 after step 1 -> escaped at step 1 (an escaping c is far from the
 //   certainly inside after step 1, outside     cardioid and the bulb, so it was not rejected): too
@@ -805,9 +805,8 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
 // spacing costs 10 % fewer iterations on in-set samples than Brent's powers of two (simulated on
 // the config-2 sample distribution: 2054 vs 2280 iterations per in-set sample, ideal 1795).
 __device__ __forceinline__ bool checkpoint_age(unsigned age) {
-  const unsigned low = age & (0u - age);
-  const unsigned rest = age ^ low;
-  return rest == 0u || rest == (low << 1);
+  const unsigned rest = age & (age - 1u);     // age without its lowest set bit
+  return rest == 0u || 3u * rest == 2u * age;  // nothing left, or the lowest bit sits right below
 }
 
 // (c) long escape tests.  Each round runs kBlock unchecked steps and tests |z|^2 once.  Because
@@ -872,12 +871,16 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       same_x = shortcut && __double_as_longlong(x) == __double_as_longlong(rx);
     } while (__ballot_sync(kFull, act && (out || same_x || age == last)) == 0u);
     {
+      // (the copy hides `age` from the compiler's induction-variable pass, which otherwise keeps
+      // `it` and last - age up to date inside the round loop: eight extra adds per round)
+      unsigned age_now = age;
+      asm volatile("" : "+r"(age_now));
       const bool cyc = same_x && __double_as_longlong(y) == __double_as_longlong(ry);
-      const bool fin = act && (out || cyc || age == last);
-      const int it = m24 - (int)(last - age) * kBlock;    // iterations done at the end of this round
+      const bool fin = act && (out || cyc || age_now == last);
+      const int it = m24 - (int)(last - age_now) * kBlock;  // iterations done at the end of this round
       const bool hit = fin && !out && (cyc || it >= max_it);  // periodic, or ran all max iterations
       const bool back = fin && !hit;                      // escaped in the round, or a short tail
-      ws.d_rounds += fin ? (int32_t)age : 0;
+      ws.d_rounds += fin ? (int32_t)age_now : 0;
       ws.d_out += (fin && out) ? 1u : 0u;
       ws.skipped += hit ? (uint32_t)(max_it - it) : 0u;
       ws.n_hit += hit ? 1u : 0u;
@@ -1008,16 +1011,26 @@ struct OrbitSpill {
   unsigned int *count;       // [0] entries written, [1] / [2] cursors of the two drain passes,
                              // [3] entries with at least kDrainLong steps left
   unsigned int capacity;
+  // Carry-over inside a pipeline of launches (tiled contexts): instead of spilling, a warp parks its
+  // < 32 leftover orbits in its own 32 slots and the same warp of the NEXT launch takes them back,
+  // so only the last launch of a render call needs the drain.
+  double4 *carry_entries;    // [warp * 32 + k]
+  int *carry_steps;
+  unsigned int *carry_count; // [warp]
+  int carry_in, carry_out;
 };
 
 // Dynamic shared memory: kWarpsPerCta WarpQueues, then (tiling only) n_tiles list entries per warp.
 constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 
-#ifndef BUDDHA_RENDER_MAXREG
-#define BUDDHA_RENDER_MAXREG 72
-#endif
-template <int kVar>
-__global__ void __maxnreg__(BUDDHA_RENDER_MAXREG)
+// Two register budgets (24 warps per SM either way).  kRegsWide = 80: the fastest render when it has
+// the SM to itself (+3 % over 72).  kRegsLean = 72 leaves 10240 registers per SM, enough for one
+// drain CTA and one apply CTA of the tiled pipeline NEXT TO the resident render CTAs: with 80 the
+// side kernels of launch k could only start when launch k+1 had finished (measured: 20000x20000
+// -m 20000 3.7e10 -> 4.4e10 samples/s, -m 2000 5.5e10 -> 7.6e10).
+constexpr int kRegsWide = 80, kRegsLean = 72;
+template <int kVar, int kMaxReg>
+__global__ void __maxnreg__(kMaxReg)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
                          unsigned long long *__restrict__ counters, OrbitSpill spill) {
@@ -1029,6 +1042,20 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   tile_counters_load(p, sink, true);
   WarpState ws;
   ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
+  if (spill.carry_in) {  // the orbits this warp parked at the end of the previous launch
+    // (the broadcast tells the compiler the count is warp-uniform: without it every vote in the
+    //  scheduler loop below is compiled with a divergence fallback, +40 % code, -5 % speed)
+    const int n = __shfl_sync(kFull, (int)spill.carry_count[sink.gwarp], 0);
+    const int k = (int)lane_id();
+    if (k < n) {
+      const double4 e = spill.carry_entries[(size_t)sink.gwarp * 32 + k];
+      const int slot = slot_of<kOrb, kZCap>(k);
+      q.z_c[slot] = make_double2(e.x, e.y); q.z_z[slot] = make_double2(e.z, e.w);
+      q.z_it[slot] = spill.carry_steps[(size_t)sink.gwarp * 32 + k];
+    }
+    ws.orb_n = n;
+    __syncwarp();
+  }
   ws.chunk_base = 0;
   ws.chunk_off = ws.chunk_len = 0;
   ws.exhausted = false;
@@ -1062,7 +1089,16 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     }
   }
   // leftovers (< 32 accepted samples): hand them to the grid-wide list
-  if (ws.orb_n > 0) {
+  if (spill.carry_out) {
+    const int k = (int)lane_id();
+    if (k < ws.orb_n) {
+      const int slot = slot_of<kOrb, kZCap>(k);
+      spill.carry_entries[(size_t)sink.gwarp * 32 + k] =
+          make_double4(q.z_c[slot].x, q.z_c[slot].y, q.z_z[slot].x, q.z_z[slot].y);
+      spill.carry_steps[(size_t)sink.gwarp * 32 + k] = q.z_it[slot];
+    }
+    if (k == 0) spill.carry_count[sink.gwarp] = (unsigned)ws.orb_n;
+  } else if (ws.orb_n > 0) {
     unsigned base = 0;
     if (lane_id() == 0) base = atomicAdd(spill.count, (unsigned)ws.orb_n);
     base = __shfl_sync(kFull, base, 0);
@@ -1113,24 +1149,21 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
-  // Two passes per launch.  The leftovers are mostly short, but one 20000-step orbit stepped by a
-  // small lane group would keep the whole launch waiting (3.7 ms at g = 1), so when the LONG
-  // entries (>= kDrainLong steps) are few enough to get a warp each, the first pass (long_pass)
-  // finishes them with g = 32 and the second takes the rest; otherwise the first pass does nothing
-  // and the second takes everything with the group size the volume allows.
-  int g = 32;
+  // Two passes per launch.  A warp steps its 32 / g orbits in lockstep until the longest is done,
+  // so a few 20000-step orbits among thousands of short ones keep whole warps spinning with one
+  // busy lane group (measured: 2.3e9 warp instructions, 4.3 ms per launch at 20000x20000
+  // -m 20000).  The first pass (long_pass) therefore takes only the entries with >= kDrainLong steps
+  // left, the second the rest; each with the largest group size g for which its entries still fit
+  // the grid twice over.
+  const unsigned n_long = min(spill.count[3], total);
   unsigned long long warps = (unsigned long long)gridDim.x * kDrainWarps;
   if (p.tile_shift && warps > p.n_warps) warps = p.n_warps;
   const unsigned long long lanes = 2ull * 32ull * warps;
-  const bool split = (unsigned long long)spill.count[3] * 32ull <= lanes;
-  int steps_lo = 0, steps_hi = 0x7fffffff;
-  if (long_pass) {
-    if (!split) return;
-    steps_lo = kDrainLong;
-  } else {
-    if (split) steps_hi = kDrainLong;
-    while (g > 1 && (unsigned long long)total * g > lanes) g >>= 1;
-  }
+  const int steps_lo = long_pass ? kDrainLong : 0, steps_hi = long_pass ? 0x7fffffff : kDrainLong;
+  const unsigned mine = long_pass ? n_long : total - n_long;
+  if (mine == 0u) return;
+  int g = 32;
+  while (g > 1 && (unsigned long long)mine * g > lanes) g >>= 1;
   const int lane = (int)lane_id();
   const int sub = lane & (g - 1), leader = lane & ~(g - 1);
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0;
@@ -1311,6 +1344,52 @@ tonemap_kernel(const uint32_t *__restrict__ hist, uint16_t *__restrict__ out, si
   }
   for (size_t k = vec * 4 + i; k < cells; k += stride)
     out[k] = tone_lookup(hist[k], lut, lut_size, thr, swap);
+}
+
+// ---- colour combine -------------------------------------------------------------------------
+//
+// generate_hires_color_image.sh:61-71 and README.md:176-185 turn three grey renders into one colour
+// image with tools outside the reference tree (image_combiner: one render per colour;
+// image_combiner_hsl: hue / saturation / lightness).  Here the three tone-mapped planes (native
+// byte order, values 0..65535) are combined on the GPU into interleaved 16-bit RGB.
+//   mode 0 (RGB): (R, G, B) = (a, b, c)
+//   mode 1 (HSL): hue = frac(a / 65535 + hue_adjust), saturation = b / 65535, lightness = c / 65535,
+//                 the usual HSL -> RGB, each component rounded to nearest
+__global__ void __launch_bounds__(256)
+combine_rgb_kernel(const uint16_t *__restrict__ a, const uint16_t *__restrict__ b,
+                   const uint16_t *__restrict__ c, uint16_t *__restrict__ rgb, size_t pixels,
+                   int mode, double hue_adjust, int swap) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
+    uint32_t r = a[i], g = b[i], bl = c[i];
+    if (mode == 1) {
+      double h = __dadd_rn(__ddiv_rn((double)r, 65535.0), hue_adjust);
+      h = __dsub_rn(h, floor(h));
+      const double sat = __ddiv_rn((double)g, 65535.0), lig = __ddiv_rn((double)bl, 65535.0);
+      const double chroma = __dmul_rn(__dsub_rn(1.0, fabs(__dsub_rn(__dmul_rn(2.0, lig), 1.0))), sat);
+      const double h6 = __dmul_rn(h, 6.0);
+      const double x = __dmul_rn(chroma, __dsub_rn(1.0, fabs(__dsub_rn(__dsub_rn(h6, __dmul_rn(2.0, floor(__dmul_rn(h6, 0.5)))), 1.0))));
+      const int sector = (int)h6;   // 0..5 (h < 1)
+      double r1 = 0.0, g1 = 0.0, b1 = 0.0;
+      switch (sector) {
+        case 0: r1 = chroma; g1 = x; break;
+        case 1: r1 = x; g1 = chroma; break;
+        case 2: g1 = chroma; b1 = x; break;
+        case 3: g1 = x; b1 = chroma; break;
+        case 4: r1 = x; b1 = chroma; break;
+        default: r1 = chroma; b1 = x; break;
+      }
+      const double m = __dsub_rn(lig, __dmul_rn(chroma, 0.5));
+      r = (uint32_t)__double2int_rn(fmin(fmax(__dmul_rn(__dadd_rn(r1, m), 65535.0), 0.0), 65535.0));
+      g = (uint32_t)__double2int_rn(fmin(fmax(__dmul_rn(__dadd_rn(g1, m), 65535.0), 0.0), 65535.0));
+      bl = (uint32_t)__double2int_rn(fmin(fmax(__dmul_rn(__dadd_rn(b1, m), 65535.0), 0.0), 65535.0));
+    }
+    if (swap) {
+      r = ((r << 8) | (r >> 8)) & 0xffffu; g = ((g << 8) | (g >> 8)) & 0xffffu;
+      bl = ((bl << 8) | (bl >> 8)) & 0xffffu;
+    }
+    rgb[3 * i] = (uint16_t)r; rgb[3 * i + 1] = (uint16_t)g; rgb[3 * i + 2] = (uint16_t)bl;
+  }
 }
 
 // ---- roofline probes --------------------------------------------------------------------------

@@ -15,6 +15,10 @@
  *   --channels M1:C1,M2:C2[,...]  fused multi-channel render: one pass over the candidates, one
  *                     histogram / -s file / PGM per (-m, -c) pair (what the three runs of
  *                     generate_hires_color_image.sh:27-59 produce); files get a .chK suffix
+ *   --color rgb|hsl   with three or more channels: also write a 16-bit colour PPM combined on the
+ *                     GPU from channels 0, 1, 2 (red/green/blue, or hue/saturation/lightness: the
+ *                     step generate_hires_color_image.sh:61-71 leaves to external tools);
+ *                     --hue-adjust X shifts the hue (the script uses 0.3)
  * With -s FILE the next sample index is kept in FILE.cursor so a resumed run continues the stream
  * instead of replaying it (the reference re-seeds with 1337 and replays).
  */
@@ -44,6 +48,8 @@ static struct {
   uint64_t samples;
   int have_first;
   uint64_t first_sample;
+  int color_mode;          /* -1 = none, BUDDHA_COMBINE_RGB, BUDDHA_COMBINE_HSL */
+  double hue_adjust;
   volatile int quit_signal_received;
   buddha_ctx *ctx[MAX_GPUS];
   uint32_t *host_buddhabrot;
@@ -146,6 +152,8 @@ static void PrintUsage(char *program_name) {
     "  --burning-ship: Render the burning ship fractal (RENDER_BURNING_SHIP in the reference).\n"
     "  --channels <m1:c1,m2:c2,...>: Render up to 4 (-m, -c) pairs in one pass; the -s and -o\n"
     "      files get a .ch<k> suffix.\n"
+    "  --color <rgb|hsl>: With 3 or more channels, also write a colour .ppm combined from\n"
+    "      channels 0, 1, 2. --hue-adjust <x> shifts the hue of the hsl mode.\n"
     "");
   exit(0);
 }
@@ -307,7 +315,20 @@ static void ParseArguments(int argc, char **argv) {
       g.params.n_channels = n;
       continue;
     }
+    if (strcmp(a, "--color") == 0) {
+      if ((i + 1) >= argc) { printf("Argument %s needs a value.\n", a); PrintUsage(argv[0]); }
+      const char *v = argv[++i];
+      if (strcmp(v, "rgb") == 0) g.color_mode = BUDDHA_COMBINE_RGB;
+      else if (strcmp(v, "hsl") == 0) g.color_mode = BUDDHA_COMBINE_HSL;
+      else { printf("--color needs rgb or hsl.\n"); PrintUsage(argv[0]); }
+      continue;
+    }
+    if (strcmp(a, "--hue-adjust") == 0) { g.hue_adjust = ParseDoubleArg(argc, argv, i++); continue; }
     printf("Invalid argument: %s\n", a);
+    PrintUsage(argv[0]);
+  }
+  if (g.color_mode >= 0 && g.params.n_channels < 3) {
+    printf("--color needs --channels with at least three max:min pairs.\n");
     PrintUsage(argv[0]);
   }
 }
@@ -460,6 +481,39 @@ static void ToneMapChannel(int k) {
   printf("Max value: %lu, scale: %f\n", (unsigned long) max, scale);
 }
 
+/* Colour PPM from channels 0, 1, 2, combined on the GPU (generate_hires_color_image.sh:61-71). */
+static void SaveColorImage(void) {
+  size_t pixel_count = (size_t) g.params.width * g.params.height;
+  const int channels[3] = {0, 1, 2};
+  uint32_t max[3];
+  char name[4096];
+  const char *dot = strrchr(g.output_image, '.');
+  if (dot && !strchr(dot, '/')) snprintf(name, sizeof(name), "%.*s.color.ppm", (int) (dot - g.output_image), g.output_image);
+  else snprintf(name, sizeof(name), "%s.color.ppm", g.output_image);
+  uint16_t *rgb = (uint16_t *) malloc(pixel_count * 3 * sizeof(uint16_t));
+  if (!rgb) {
+    printf("Failed allocating the colour image.\n");
+    return;
+  }
+  Check(buddha_combine_rgb_u16(g.ctx[0], channels, g.gamma_correction, g.color_mode, g.hue_adjust, 1,
+    rgb, pixel_count, max), g.ctx[0], "Combining the colour image");
+  FILE *output = fopen(name, "wb");
+  if (!output) {
+    printf("Failed opening output image.\n");
+    free(rgb);
+    return;
+  }
+  if (fprintf(output, "P6\n%d %d\n%d\n", g.params.width, g.params.height, 0xffff) <= 0 ||
+      !fwrite(rgb, pixel_count * 3 * sizeof(uint16_t), 1, output)) {
+    printf("Failed writing the colour image.\n");
+  } else {
+    printf("Colour image (%s of channels 0, 1, 2) saved: %s\n",
+      g.color_mode == BUDDHA_COMBINE_HSL ? "hue/saturation/lightness" : "red/green/blue", name);
+  }
+  fclose(output);
+  free(rgb);
+}
+
 /* ---- rendering --------------------------------------------------------------------------- */
 
 typedef struct {
@@ -547,6 +601,7 @@ int main(int argc, char **argv) {
   g.seconds_to_run = 10.0;
   g.gamma_correction = 1.0;
   g.gpus = 1;
+  g.color_mode = -1;
   ParseArguments(argc, argv);
   if (signal(SIGINT, SignalHandler) == SIG_ERR) {
     printf("Failed setting signal handler.\n");
@@ -596,6 +651,7 @@ int main(int argc, char **argv) {
       SaveImage(name);
     }
   }
+  if (g.color_mode >= 0) SaveColorImage();
   printf("Done! Output image saved: %s\n", g.output_image);
   Cleanup();
   return 0;

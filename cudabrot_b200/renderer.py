@@ -171,6 +171,20 @@ class Renderer:
                                                           out.size, C.byref(mx), C.byref(sc)))
         return out, mx.value, sc.value
 
+    def combine_rgb(self, channels=(0, 1, 2), gamma=1.0, mode="rgb", hue_adjust=0.0,
+                    big_endian=False, out=None):
+        """uint16[h, w, 3] colour image from three channels, combined on the GPU; mode "rgb" or
+        "hsl" (hue, saturation, lightness = the three channels).  Returns (image, [max per channel])."""
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.uint16)
+        ch = (C.c_int * 3)(*channels)
+        mx = (C.c_uint32 * 3)()
+        self._check(self._lib.buddha_combine_rgb_u16(self._ctx, ch, gamma,
+                                                     {"rgb": 0, "hsl": 1}[mode], hue_adjust,
+                                                     int(big_endian), out.ctypes.data,
+                                                     self.width * self.height, mx))
+        return out, [int(v) for v in mx]
+
     def digest(self, channel=0):
         """64-bit blocked FNV-1a digest of one channel, formed on the GPU (include/buddha.h)."""
         d = C.c_uint64()

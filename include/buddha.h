@@ -188,6 +188,22 @@ int buddha_tonemap_snapshot_u16(buddha_ctx *ctx, int channel, double gamma, int 
                                 uint16_t *host_out, size_t cells, uint32_t *max_out,
                                 double *scale_out);
 
+/* Colour image from three channels, on the GPU.  generate_hires_color_image.sh:61-71 and
+ * README.md:176-185 do this with tools outside the reference tree (ImageMagick, image_combiner,
+ * image_combiner_hsl), so there is no byte-level reference; the definition is:
+ * each channels[k] (an index into this context's channels; indices may repeat) is tone-mapped with
+ * `gamma` and scaled by its own maximum exactly as buddha_tonemap_channel_u16 does, then
+ *   BUDDHA_COMBINE_RGB: (R, G, B) = the three grey values
+ *   BUDDHA_COMBINE_HSL: hue = frac(g0 / 65535 + hue_adjust), saturation = g1 / 65535, lightness =
+ *                       g2 / 65535, standard HSL -> RGB in double precision, rounded to nearest.
+ * host_rgb receives pixels * 3 uint16 (interleaved; big_endian != 0: PPM "P6 ... 65535" byte order).
+ * max_out (may be NULL) receives the three maxima. */
+#define BUDDHA_COMBINE_RGB 0
+#define BUDDHA_COMBINE_HSL 1
+int buddha_combine_rgb_u16(buddha_ctx *ctx, const int channels[3], double gamma, int mode,
+                           double hue_adjust, int big_endian, uint16_t *host_rgb, size_t pixels,
+                           uint32_t max_out[3]);
+
 /* 64-bit digest of one channel of the histogram (channel 0 of a plain context), formed on the GPU:
  * equal histograms give equal digests, so "N GPUs == 1 GPU == CPU restatement" can be checked on 1.6 GB
  * canvases without moving them.  Definition (restated in numpy by the tests, blocked_fnv):

@@ -632,3 +632,64 @@ def test_production_tiles_cfg5_fused_and_cfg3_m20000(buddha, oracle):
         r.render_samples(1 << 20, n - (1 << 20))
         assert r.digest() == oracle.blocked_fnv(ohist)
         assert_same(r.read_histogram(), r.counters(), ohist, ocnt)
+
+
+def test_colour_combine_matches_numpy_restatement(buddha, oracle):
+    """buddha_combine_rgb_u16 (the step generate_hires_color_image.sh:61-71 leaves to external
+    tools): RGB = the three tone-mapped channels, bit for bit; HSL = the standard HSL -> RGB in
+    double precision on the oracle's tone-mapped planes (tolerance: 1 of 65535, the rounding of
+    the last multiplication may differ between libm-free device code and numpy)."""
+    chans = [(100, 20), (1000, 20), (5000, 20)]
+    w, h, n = 400, 300, 1 << 21
+    planes = []
+    for (m, c) in chans:
+        ohist, _, _ = oracle.render(w, h, m, c, 1337, 0, n)
+        img, mx, _ = oracle.tonemap(ohist, 2.2)
+        planes.append((img.astype(np.float64), mx, img))
+    with buddha.Renderer(w, h, channels=chans) as r:
+        r.render_samples(0, n)
+        rgb, mx = r.combine_rgb((2, 1, 0), gamma=2.2, mode="rgb")
+        assert mx == [planes[2][1], planes[1][1], planes[0][1]]
+        for k, ch in enumerate((2, 1, 0)):
+            assert np.array_equal(rgb[:, :, k], planes[ch][2])
+        be, _ = r.combine_rgb((2, 1, 0), gamma=2.2, mode="rgb", big_endian=True)
+        assert np.array_equal(be.byteswap(), rgb)
+        hsl, _ = r.combine_rgb((1, 0, 2), gamma=2.2, mode="hsl", hue_adjust=0.3)
+        with pytest.raises(buddha.BuddhaError):
+            r.combine_rgb((0, 1, 7))
+    hue = (planes[1][0] / 65535.0 + 0.3) % 1.0
+    sat, lig = planes[0][0] / 65535.0, planes[2][0] / 65535.0
+    chroma = (1.0 - np.abs(2.0 * lig - 1.0)) * sat
+    h6 = hue * 6.0
+    x = chroma * (1.0 - np.abs(h6 % 2.0 - 1.0))
+    sector = h6.astype(np.int64)
+    zero = np.zeros_like(chroma)
+    r1 = np.choose(sector, [chroma, x, zero, zero, x, chroma])
+    g1 = np.choose(sector, [x, chroma, chroma, x, zero, zero])
+    b1 = np.choose(sector, [zero, zero, x, chroma, chroma, x])
+    m = lig - chroma * 0.5
+    want = np.stack([np.rint(np.clip((v + m) * 65535.0, 0, 65535)) for v in (r1, g1, b1)], axis=2)
+    diff = np.abs(hsl.astype(np.int64) - want.astype(np.int64))
+    assert diff.max() <= 1
+    assert (diff == 0).mean() > 0.999
+
+
+def test_cli_colour_ppm(buddha, tmp_path):
+    """--color rgb: the PPM is the three channel PGMs interleaved (P6, 16-bit big-endian)."""
+    cli = buddha.capi.CLI_PATH
+    out = str(tmp_path / "img.pgm")
+    r = subprocess.run([cli, "-w", "120", "-h", "80", "--channels", "100:20,1000:20,5000:20",
+                        "--color", "rgb", "-g", "2.2", "-o", out, "--samples", "300000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ppm = open(str(tmp_path / "img.color.ppm"), "rb").read()
+    head = b"P6\n120 80\n65535\n"
+    assert ppm.startswith(head)
+    rgb = np.frombuffer(ppm[len(head):], dtype=">u2").reshape(80, 120, 3)
+    for k in range(3):
+        pgm = open(str(tmp_path / ("img.ch%d.pgm" % k)), "rb").read()
+        grey = np.frombuffer(pgm[len(b"P5\n120 80\n65535\n"):], dtype=">u2").reshape(80, 120)
+        assert np.array_equal(rgb[:, :, k], grey)
+    r = subprocess.run([cli, "--color", "rgb", "--samples", "10"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "--color needs --channels" in r.stdout
