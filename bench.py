@@ -323,6 +323,10 @@ def make_red_roofline(r, cnt, scale, t_s, hist_bytes, tiled, workload):
     reduction inside an L2-resident 64 MB tile, so the ceiling is the in-L2 reduction rate."""
     inc = cnt["increments"] * scale
     foot = min(hist_bytes, 64 << 20) if tiled else hist_bytes
+    copies = 1
+    if hist_bytes <= (128 << 10):   # the library's rule for privatised copies (buddha_api.cu)
+        copies = min(64, (4 << 20) // hist_bytes)
+        foot = hist_bytes * copies
     peak = r.probe_red_peak(foot)
     out = {"bound": "l2-red", "unit": "Gred/s", "achieved": inc / t_s / 1e9, "peak": peak / 1e9,
            "frac": inc / t_s / peak, "footprint_bytes": hist_bytes, "tiled_scatter": bool(tiled),
@@ -330,6 +334,8 @@ def make_red_roofline(r, cnt, scale, t_s, hist_bytes, tiled, workload):
                           "array (%s)" % (foot >> 20, "one L2-resident tile" if tiled else
                                           "the histogram's size"),
            "algorithmic_bytes_per_increment": 4}
+    if copies > 1:
+        out["privatised_copies"] = copies
     if tiled:
         # HBM bytes the tiled pipeline has to move: the list entry written and read back (8 B per
         # increment) plus one read and one write-back of every 64 MB tile per pipeline launch

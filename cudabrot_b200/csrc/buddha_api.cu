@@ -431,8 +431,17 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   CUC(cudaEventCreate(&c->ev_ta));
   CUC(cudaEventCreate(&c->ev_tb));
   c->dev_cells = c->ch_cells * (size_t)(n_ch > 1 ? c->n_bands : 1);
-  CUC(cudaMalloc(&c->d_hist, c->dev_cells * sizeof(uint32_t)));
-  CUC(cudaMemsetAsync(c->d_hist, 0, c->dev_cells * sizeof(uint32_t), c->stream));
+  // tiny single-channel canvases get privatised copies (RenderParams::n_copies): up to 64 of
+  // them, together at most 4 MB
+  c->rp.n_copies = 1;
+  c->rp.copy_stride = 0;
+  if (n_ch == 1 && !c->tiled && !(p->flags & BUDDHA_F_SIMPLE_KERNEL) &&
+      c->dev_cells * sizeof(uint32_t) <= (128u << 10)) {
+    c->rp.n_copies = (uint32_t)std::min<size_t>(64, ((size_t)4 << 20) / (c->dev_cells * sizeof(uint32_t)));
+    c->rp.copy_stride = (uint32_t)c->dev_cells;
+  }
+  CUC(cudaMalloc(&c->d_hist, c->dev_cells * c->rp.n_copies * sizeof(uint32_t)));
+  CUC(cudaMemsetAsync(c->d_hist, 0, c->dev_cells * c->rp.n_copies * sizeof(uint32_t), c->stream));
   CUC(cudaMalloc(&c->d_cursor, sizeof(unsigned long long)));
   CUC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kTotalCnt));
   CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kTotalCnt, c->stream));
@@ -810,7 +819,16 @@ static int enqueue_render(buddha_ctx *c, uint64_t first, uint64_t count) {
   if (first + count < first || first + count > ~(uint64_t)0 - slack)
     return fail(c, BUDDHA_EINVAL, "sample range must end below 2^64 - %llu",
                 (unsigned long long)slack);
-  if (!c->tiled) return launch_render(c, first, count);
+  if (!c->tiled) {
+    int rc = launch_render(c, first, count);
+    if (rc == BUDDHA_OK && c->rp.n_copies > 1) {
+      fold_copies_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->d_hist, c->dev_cells, c->rp.n_copies,
+                                                             c->rp.copy_stride);
+      CU(c, cudaGetLastError());
+      c->launches += 1;
+    }
+    return rc;
+  }
   if (!c->tile_calibrated) {
     uint64_t n0 = std::min<uint64_t>(count, (uint64_t)1 << 22);
     int rc = calibrate_tiles(c, first, n0);

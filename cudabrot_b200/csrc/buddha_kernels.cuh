@@ -98,6 +98,12 @@ struct RenderParams {
   int32_t seg_start[2 * kMaxChannels + 1];  // segment s covers steps seg_start[s] .. seg_start[s+1]-1
   int32_t seg_band[2 * kMaxChannels];       // its band, or -1 if no channel accepts there
   uint32_t band_stride;         // cells per band (= w * h)
+  // Privatised copies for tiny canvases (north_star (d)): when every orbit point lands in a few
+  // thousand cells, reductions to the same address serialise in L2 (64x64: 1.9e10 samples/s
+  // against 1.0e11 from 256x256 up, profiles/r02_dense_canvas.txt).  CTA b then adds into copy
+  // b % n_copies of the histogram (copy k at hist + k * copy_stride, all of them L2-resident) and
+  // fold_copies_kernel sums them into copy 0 after every render call.  1 = off.
+  uint32_t n_copies, copy_stride;
   uint32_t key0[10], key1[10];  // Philox round keys: key + r * (W0, W1)
   unsigned long long end;       // one past the last sample index of this launch
   uint32_t chunk;               // sample indices a warp takes per cursor grab (multiple of 32):
@@ -1037,7 +1043,8 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpQueues &q = reinterpret_cast<WarpQueues *>(smem_raw)[threadIdx.x >> 5];
   uint2 *tile_tab = reinterpret_cast<uint2 *>(smem_raw + kQueueBytes);
-  const Sink sink = {hist, tile_tab + (threadIdx.x >> 5) * p.n_tiles,
+  const Sink sink = {hist + (size_t)(blockIdx.x % p.n_copies) * p.copy_stride,
+                     tile_tab + (threadIdx.x >> 5) * p.n_tiles,
                      blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
   tile_counters_load(p, sink, true);
   WarpState ws;
@@ -1278,6 +1285,20 @@ digest_blocks_kernel(const uint32_t *__restrict__ hist, size_t cells,
     unsigned long long d = kFnvBasis;
     for (int l = 0; l < 32; l++) d = (d ^ __shfl_sync(kFull, h, l)) * kFnvPrime;
     if (lane == 0) block_digest[b] = d;
+  }
+}
+
+// Privatised copies (RenderParams::n_copies): hist[i] += copies 1 .. n-1, which are cleared.
+__global__ void __launch_bounds__(256)
+fold_copies_kernel(uint32_t *__restrict__ hist, size_t cells, uint32_t n_copies, size_t stride) {
+  size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += step) {
+    uint32_t v = hist[i];
+    for (uint32_t k = 1; k < n_copies; k++) {
+      v += hist[k * stride + i];
+      hist[k * stride + i] = 0u;
+    }
+    hist[i] = v;
   }
 }
 
