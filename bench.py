@@ -68,9 +68,9 @@ CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)],
             "cfg5_4k": [(100, 20), (1000, 20), (20000, 20)]}
 REFERENCE_PASS = 13107200  # 512 blocks * 512 threads * 50 samples, cudabrot.cu:20,23,34
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_persistent_kernel launch over 2^30
-# samples, from the `ncu --set full` captures summarised in profiles/r01_summary.md
-NCU_DRAM_BYTES_PER_2P30_LAUNCH = {"cfg1": 4037888 + 1280, "cfg2": 37888 + 256,
-                                  "cfg3": 208894976 + 5066775000}
+# samples, from the `ncu --set full` captures summarised in profiles/r02_summary.md
+NCU_DRAM_BYTES_PER_2P30_LAUNCH = {"cfg1": 4038912 + 5376, "cfg2": 39680 + 0,
+                                  "cfg3": 255045120 + 5058764000, "cfg4": 127435520 + 2082458000}
 METRIC = "candidate samples/sec"
 
 
@@ -268,13 +268,15 @@ def reference_arm(args, wl, rank):
 
 # ---- roofline model --------------------------------------------------------------------------
 # FP64-pipe warp instructions the render kernel EXECUTES, as lane-instructions per unit of work,
-# calibrated against ncu (sm__inst_executed_pipe_fp64 of render_persistent_kernel, 2^30-sample
-# launches, profiles/r02_render_cfg{1,2}_ncu_raw_selected.csv): a per candidate (Philox
-# coordinates 4, cardioid/bulb 9, two tested steps 14, plus the tiers' re-computed prefixes and
-# tested steps), b per escape-pass iteration actually executed (4 per unchecked deep step, 7 per
-# tested step, idle lanes and rolled-back rounds included), c per recorded orbit point (step 4 +
-# division-free binning 4, at the orbit phase's >= 87.5 % lane occupancy).
-FP64_MODEL = {"per_candidate": 34.7, "per_executed_iteration": 4.36, "per_orbit_point": 8.6}
+# calibrated against ncu (executed DFMA / DMUL / DADD / DSETP of render_persistent_kernel from the
+# source pages of `ncu --set full` captures over 2^30-sample launches, profiles/r02_summary.md):
+# a per candidate (the exact tiers' coordinates, cardioid/bulb test, re-computed prefixes and
+# tested steps for the 17.5 % of the candidates the FP32 pre-classification does not retire), b per
+# escape-pass iteration actually executed (4 per unchecked deep step, 7 per tested step, idle
+# lanes and rolled-back rounds included), c per recorded orbit point (step 4 + division-free
+# binning 4, at the orbit phase's lane occupancy).  Fit of the round-2 kernel: config 1 34.6
+# (model 34.6), config 2 98.4 (98.3), config 3 67.4 (66.3), config 4 82.3 (82.9) per candidate.
+FP64_MODEL = {"per_candidate": 17.0, "per_executed_iteration": 4.46, "per_orbit_point": 8.6}
 HW_FP64_LANES = 148 * 64  # FP64 lanes of one B200: the hardware issue rate is this x the SM clock
 
 
@@ -522,6 +524,9 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
         host_hist = pinned(cells, "uint32").reshape((n_ch, h, w) if channels else (h, w))
         host_img = pinned(cells, "uint16")
     ranges = [step_range(k, rank, world, per_gpu, first=1 << 57) for k in range(n_e2e)]
+    # one short untimed pass first: the staging / snapshot / scratch buffers are allocated on first use
+    e2e_pipeline(r, [step_range(0, rank, world, 1 << 22, first=1 << 58)], host_in, host_hist, host_img,
+                 n_ch, (h, w), rank, world, hist_t, dist)
     cx.barrier()
     e2e_s = e2e_pipeline(r, ranges, host_in, host_hist, host_img, n_ch, (h, w), rank, world,
                          hist_t, dist)

@@ -595,3 +595,57 @@ uint64_t oracle_check_prefilter(uint64_t seed, uint64_t first, uint64_t count, i
   if (counts) { counts[0] = c0; counts[1] = c1; counts[2] = c2; counts[3] = c3; }
   return bad;
 }
+
+/* A period-4 test of the same kind (derived and measured in round 2, not enabled in the kernel:
+ * DESIGN.md section 5), in float: Newton
+ * from 0 on mu^3 - (3 - c^2) mu^2 + (3 + c^2 - c^3 - c^4) mu - (1 + 2c^2 + 3c^3 + 3c^4 + 3c^5 + c^6)
+ * (mu = lambda / 16), accepted if |mu| + 3 |p / p'| < mu_max. */
+typedef struct { float r, i; } cfl;
+static inline cfl cfl_mul(cfl a, cfl b) { cfl o = {fmaf(a.r, b.r, -a.i * b.i), fmaf(a.r, b.i, a.i * b.r)}; return o; }
+static inline cfl cfl_add(cfl a, cfl b) { cfl o = {a.r + b.r, a.i + b.i}; return o; }
+static inline cfl cfl_div(cfl a, cfl b) {
+  const float d = 1.0f / fmaf(b.r, b.r, b.i * b.i);
+  cfl o = {fmaf(a.r, b.r, a.i * b.i) * d, fmaf(a.i, b.r, -a.r * b.i) * d};
+  return o;
+}
+int oracle_period4_flag(double c_real, double c_imag, float mu_max) {
+  const cfl c = {(float)c_real, (float)c_imag};
+  const cfl c2 = cfl_mul(c, c), c3 = cfl_mul(c2, c), c4 = cfl_mul(c2, c2), c5 = cfl_mul(c4, c), c6 = cfl_mul(c3, c3);
+  const cfl a2 = {c2.r - 3.0f, c2.i};
+  const cfl a1 = {3.0f + c2.r - c3.r - c4.r, c2.i - c3.i - c4.i};
+  const cfl a0 = {-(1.0f + 2.0f * c2.r + 3.0f * (c3.r + c4.r + c5.r) + c6.r),
+                  -(2.0f * c2.i + 3.0f * (c3.i + c4.i + c5.i) + c6.i)};
+  cfl mu = {0.0f, 0.0f}, p = a0, dp = a1;
+  for (int k = 0; k < 4; k++) {
+    const cfl q = cfl_div(p, dp);
+    mu.r -= q.r; mu.i -= q.i;
+    p = cfl_add(cfl_mul(cfl_add(cfl_mul(cfl_add(mu, a2), mu), a1), mu), a0);
+    cfl t3 = {3.0f * mu.r, 3.0f * mu.i}, t2 = {2.0f * a2.r, 2.0f * a2.i};
+    dp = cfl_add(cfl_mul(cfl_add(t3, t2), mu), a1);
+  }
+  const cfl q = cfl_div(p, dp);
+  const float bound = sqrtf(fmaf(mu.r, mu.r, mu.i * mu.i)) + 3.0f * sqrtf(fmaf(q.r, q.r, q.i * q.i));
+  return bound < mu_max;
+}
+
+/* Like oracle_check_period3, for the period-4 test: flagged samples that escaped (must be 0). */
+uint64_t oracle_check_period4(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                              float mu_max, uint64_t *flagged, uint64_t *inset) {
+  uint64_t bad = 0, fl = 0, in = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : bad, fl, in)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    if (oracle_rejected(cre, cim)) continue;
+    int f = oracle_period4_flag(cre, cim, mu_max);
+    if (!f && inset == NULL) continue;
+    int it = oracle_escape_iterations(cre, cim, max_iterations);
+    if (it >= max_iterations) in++;
+    if (f) { fl++; if (it < max_iterations) bad++; }
+  }
+  if (flagged) *flagged = fl;
+  if (inset) *inset = in;
+  return bad;
+}

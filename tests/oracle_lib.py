@@ -202,6 +202,18 @@ def check_period3(seed, first, count, max_iter, limit=0.96):
     return int(bad), fl.value, ins.value
 
 
+def check_period4(seed, first, count, max_iter, mu_max=0.98 / 16):
+    """Like check_period3 for the period-4 multiplier cubic (not enabled in the
+    kernel)."""
+    L = lib()
+    L.oracle_check_period4.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_float,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.oracle_check_period4.restype = C.c_uint64
+    fl, ins = C.c_uint64(), C.c_uint64()
+    bad = L.oracle_check_period4(seed, first, count, max_iter, mu_max, C.byref(fl), C.byref(ins))
+    return int(bad), fl.value, ins.value
+
+
 def check_prefilter(seed, first, count, ship=False, m_rej=0.02, m_esc=0.05):
     """(decided samples that disagree with the reference's arithmetic -- must be 0, [undecided,
     rejected, escapes at step 1, at step 2]): the evidence behind the sampler's FP32
