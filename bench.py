@@ -406,11 +406,20 @@ class Ctx:
         self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
         self.torch, self.dist = torch, dist
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        # host-side barrier (gloo): while rank 0 runs another PROCESS on all GPUs (cli_merge_check)
+        # the other ranks must not sit in an NCCL barrier kernel -- the GPU would time-slice the
+        # two processes and the other process's collectives crawl
+        self.host_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
 
     def allmax(self, *vals):
         if self.world == 1:
@@ -685,9 +694,9 @@ def native_arm(args, wl, rank, world, local_rank):
     extras, strong, cli = [], None, None
     if not args.no_extras:
         strong = run_strong(cx, n_total=args.strong_samples)
-        cx.barrier()
+        cx.host_barrier()
         cli = cli_merge_check(cx)
-        cx.barrier()
+        cx.host_barrier()
         for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
             if name == args.workload:
                 continue

@@ -72,6 +72,7 @@ enum CounterSlot {
 // fused render: accumulators that follow the kCntSlots common ones, kChSlots per index; kChHit and
 // kChOver are indexed by CHANNEL, the other three by BAND (see RenderParams)
 enum ChannelSlot { kChHit = 0, kChOver, kChAccepted, kChPoints, kChIncrements, kChSlots };
+constexpr int kChCount = (kMaxBands * kChSlots + 1) & ~1;   // accumulators per warp (even: 16-byte size)
 
 struct RenderParams {
   // canvas in the reference's form (exact binning path), cudabrot.cu:46-58
@@ -409,6 +410,10 @@ struct WarpQueues {
   uint2 deep_meta[kDeepCap];
   int z_it[kZCap];
   int pad[(4 - (2 * kDeepCap + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
+  // fused render: this warp's per-channel / per-band accumulators (ChannelSlot), added to the
+  // global ones when the kernel ends.  (They used to be global atomics from every late / tier
+  // batch: 6 same-address atomics per ~1000 candidates from 10 000 warps.)
+  unsigned long long ch_cnt[kChCount];
 };
 static_assert(sizeof(WarpQueues) % 16 == 0, "stack arrays must stay 16-byte aligned");
 
@@ -472,20 +477,20 @@ __device__ __forceinline__ void flush_counters(WarpState &ws, unsigned long long
 }
 
 // Adds v (summed over the warp) to one per-channel accumulator; called from rare branches only.
-__device__ __forceinline__ void channel_add(unsigned long long *counters, int ch, int slot,
-                                            uint32_t v) {
+// chc = the warp's accumulators in shared memory (render kernel) or the global ones (drain).
+__device__ __forceinline__ void channel_add(unsigned long long *chc, int ch, int slot, uint32_t v) {
   v = __reduce_add_sync(kFull, v);
-  if (lane_id() == 0 && v) atomicAdd(counters + kCntSlots + ch * kChSlots + slot, (unsigned long long)v);
+  if (lane_id() == 0 && v) atomicAdd(chc + ch * kChSlots + slot, (unsigned long long)v);
 }
 
 // Fused render: the per-channel increment counters.
 template <int kVar>
 __device__ __forceinline__ void flush_channel_counters(const RenderParams &p, WarpState &ws,
-                                                       unsigned long long *counters) {
+                                                       unsigned long long *chc) {
   if constexpr ((kVar & kVarFused) != 0) {
 #pragma unroll
     for (int k = 0; k < kMaxBands; k++) {
-      if (k < p.n_bands) channel_add(counters, k, kChIncrements, ws.ch_inc[k]);
+      if (k < p.n_bands) channel_add(chc, k, kChIncrements, ws.ch_inc[k]);
       ws.ch_inc[k] = 0;
     }
   }
@@ -541,9 +546,8 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
       const bool a = code == (unsigned)(k + 1);
       const unsigned n = __popc(__ballot_sync(kFull, a));
       if (n == 0u) continue;
-      if (lane_id() == 0)
-        atomicAdd(counters + kCntSlots + k * kChSlots + kChAccepted, (unsigned long long)n);
-      channel_add(counters, k, kChPoints, a ? (uint32_t)it : 0u);
+      if (lane_id() == 0) q.ch_cnt[k * kChSlots + kChAccepted] += n;
+      channel_add(q.ch_cnt, k, kChPoints, a ? (uint32_t)it : 0u);
     }
     n |= (int)((code - 1u) << kOrbStepBits);
   }
@@ -555,8 +559,8 @@ __device__ __forceinline__ void push_orbit(const RenderParams &p, WarpQueues &q,
 // min(it_f, ch_max[k])).  Samples that never escape hit every channel's limit; the host adds
 // those from the common hit counter (buddha_get_channel_counters), so deep stays untouched.
 template <int kVar>
-__device__ __forceinline__ void channel_finish(const RenderParams &p, unsigned long long *counters,
-                                               bool esc, int it_f) {
+__device__ __forceinline__ void channel_finish(const RenderParams &p, WarpQueues &q, bool esc,
+                                               int it_f) {
   if constexpr ((kVar & kVarFused) != 0) {
     const bool any = esc && it_f > p.ch_low;
     if (__ballot_sync(kFull, any) == 0u) return;
@@ -564,8 +568,8 @@ __device__ __forceinline__ void channel_finish(const RenderParams &p, unsigned l
       const bool over = any && it_f > p.ch_max[k];
       const unsigned n = __popc(__ballot_sync(kFull, over));
       if (n == 0u) continue;
-      if (lane_id() == 0) atomicAdd(counters + kCntSlots + k * kChSlots + kChHit, (unsigned long long)n);
-      channel_add(counters, k, kChOver, over ? (uint32_t)(it_f - p.ch_max[k]) : 0u);
+      if (lane_id() == 0) q.ch_cnt[k * kChSlots + kChHit] += n;
+      channel_add(q.ch_cnt, k, kChOver, over ? (uint32_t)(it_f - p.ch_max[k]) : 0u);
     }
   }
 }
@@ -621,7 +625,7 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
         for (int k = 0; k < kMaxBands; k++) any |= ws.ch_inc[k];
         if (__ballot_sync(kFull, (any >> 29) != 0u)) {
           flush_counters(ws, counters);
-          flush_channel_counters<kVar>(p, ws, counters);
+          flush_channel_counters<kVar>(p, ws, q.ch_cnt);
         }
       }
       unsigned long long base = 0;
@@ -783,7 +787,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   const bool hit = surv && nit >= p.max_it;  // ran all max iterations (allowed == max - it)
   ws.n_hit += hit ? 1u : 0u;
   push_orbit<kVar>(p, q, ws, counters, esc, cx, cy, it + cnt);
-  channel_finish<kVar>(p, counters, esc, it + cnt);
+  channel_finish<kVar>(p, q, esc, it + cnt);
   const bool cont = surv && !hit;
   if (__ballot_sync(kFull, cont)) {
     // samples well inside a period-3 component never escape: hit max without iterating
@@ -1047,6 +1051,10 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                      tile_tab + (threadIdx.x >> 5) * p.n_tiles,
                      blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)};
   tile_counters_load(p, sink, true);
+  if constexpr ((kVar & kVarFused) != 0) {
+    for (int k = (int)lane_id(); k < kChCount; k += 32) q.ch_cnt[k] = 0ull;
+    __syncwarp();
+  }
   WarpState ws;
   ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
   if (spill.carry_in) {  // the orbits this warp parked at the end of the previous launch
@@ -1123,7 +1131,12 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
-  flush_channel_counters<kVar>(p, ws, counters);
+  if constexpr ((kVar & kVarFused) != 0) {
+    flush_channel_counters<kVar>(p, ws, q.ch_cnt);
+    __syncwarp();
+    for (int k = (int)lane_id(); k < kMaxBands * kChSlots; k += 32)
+      if (q.ch_cnt[k]) atomicAdd(counters + kCntSlots + k, q.ch_cnt[k]);
+  }
 }
 
 // Finishes the spilled orbits.  The leftovers are few but up to max_it steps long, so their cost is
@@ -1213,7 +1226,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
   }
   tile_counters_store(p, sink);
   flush_counters(ws, counters);
-  flush_channel_counters<kVar>(p, ws, counters);
+  flush_channel_counters<kVar>(p, ws, counters + kCntSlots);
 }
 
 // Applies the lists of ONE tile: warp w owns list (t, w).  One launch per tile keeps every
