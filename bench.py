@@ -533,6 +533,7 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
         host_hist = pinned(cells, "uint32").reshape((n_ch, h, w) if channels else (h, w))
         host_img = pinned(cells, "uint16")
     ranges = [step_range(k, rank, world, per_gpu, first=1 << 57) for k in range(n_e2e)]
+    inc_before = r.counters()["increments"]
     # one short untimed pass first: the staging / snapshot / scratch buffers are allocated on first use
     e2e_pipeline(r, [step_range(0, rank, world, 1 << 22, first=1 << 58)], host_in, host_hist, host_img,
                  n_ch, (h, w), rank, world, hist_t, dist)
@@ -542,6 +543,12 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
     cx.barrier()
     (e2e_s,) = cx.allmax(e2e_s)
     e2e_value = per_gpu * n_e2e * world / e2e_s
+    # the histogram that came back over PCIe must hold exactly what all ranks counted meanwhile
+    _, (inc_e2e,) = cx.allsum_counters(r.counters(), extra=(r.counters()["increments"] - inc_before,))
+    if rank == 0 and not channels:
+        got = int(host_hist.sum(dtype=np.uint64))
+        if got != inc_e2e:
+            raise RuntimeError("%s: e2e histogram sum %d != increments %d" % (name, got, inc_e2e))
 
     if rank != 0:
         r.close()

@@ -376,7 +376,7 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
   fill_render_params(c);
 
   int per_sm = 0;
-  // the work stacks are dynamic shared memory (110 KB per CTA: opt-in above 48 KB)
+  // the work stacks are dynamic shared memory (66 KB per CTA: opt-in above 48 KB)
   c->render_smem = kQueueBytes;
   if (const char *e = getenv("BUDDHA_PAD_SMEM")) c->smem_pad = (size_t)atoi(e);  // occupancy experiments
   c->variant = ((p->flags & BUDDHA_F_BURNING_SHIP) ? kVarShip : 0) | (n_ch > 1 ? kVarFused : 0);

@@ -38,7 +38,7 @@ constexpr int kCtasPerSm = BUDDHA_CTAS_PER_SM;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 // Work stacks (entries).  A phase pops at most 32 entries and pushes at most 32, and runs only
 // while its targets hold < 32, so no stack exceeds 63.  `late` and `orb` share one array and grow
-// towards each other, and so do `t1` and `t2`: t1 + t2 <= 63 + 31, and late + orb <= kZJoint + 32
+// towards each other, and so do `t0` and `t2`: t0 + t2 <= 63 + 31, and late + orb <= kZJoint + 32
 // because every phase that pushes to them starts only while late + orb <= kZJoint (else `late`
 // runs first, with whatever it holds).
 constexpr int kDeepCap = 63;
@@ -375,11 +375,12 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 // TIERS: all 32 lanes run the same number of steps with the exact per-step test and no per-lane
 // refill, survivors are ballot-compacted onto the next stack.  The survival curve is so flat
 // (33 % survive step 1, 19 % step 2, 6.5 % step 6, 2.3 % step 22, 1.5 % step 46) that a tier
-// keeps 55..78 % of its lane-steps useful, while the bookkeeping per step drops to one predicated
+// keeps most of its lane-steps useful, while the bookkeeping per step drops to one predicated
 // add and one predicate update.
 //
-//   gen     draw 32 candidates (Philox), cardioid/bulb test, steps 1..2      -> t1 (c only)
-//   tier 1  steps 3..6  (re-computes steps 1..2 from c: 8 FP64, saves 16 B)  -> t2 (c only)
+//   gen     draw 32 candidates (Philox); FP32 pre-classification retires the certainly rejected
+//           and the certain step-1 / step-2 escapes (82 %) without FP64   -> t0 (Philox words)
+//   tier 0  c from the words in FP64, exact cardioid/bulb test, steps 1..6 -> t2 (c only)
 //   tier 2  steps 7..22 (re-computes steps 1..6)                             -> late
 //   late    24 per-step-tested steps from a stored state (c, z, it): tier-2 survivors, samples
 //           handed back by deep, tails that have fewer than kBlock steps left -> deep / late
@@ -389,9 +390,9 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 //   orbit   re-iterate accepted samples for exactly i+1 steps and scatter with red.global.add.
 //
 // Every tier may also push accepted escapes to `orbit`.  The scheduler serves the stacks in the
-// order orbit, late, deep, t2, t1, gen; a phase runs only while each stack it pushes to holds
-// < 32 entries (late re-queues its own survivors while deep is full), so the 64-entry stacks
-// cannot overflow and some phase can always run.
+// order orbit, late, deep, t2, t0, gen; a phase runs only while each stack it pushes to holds
+// < 32 entries (late re-queues its own survivors while deep is full), so no stack exceeds 63
+// entries and some phase can always run.
 //
 // Lanes that have escaped keep stepping until their tier ends; their values grow to inf/NaN,
 // which no later code reads (the `alive` predicate is sticky and NaN compares false).

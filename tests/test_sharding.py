@@ -73,3 +73,17 @@ def test_two_rank_merge_equals_single_render(oracle, tmp_path):
     expect[0, 0] += np.uint32(4)            # 5 + 0xFFFFFFFF wraps to 4
     expect[0, 1] += np.uint32(0x80000002)   # 3 + 0x7FFFFFFF
     assert np.array_equal(merged, expect)
+
+
+def test_bench_arms_share_config_and_model_is_sane():
+    """Both bench arms must print the same `config` dict (the driver compares them), and the
+    executed-FP64 model must reproduce the ncu counts it was fitted to (profiles/r02_summary.md)."""
+    import bench
+    for name, wl in bench.WORKLOADS.items():
+        assert bench.make_config(name, wl) == bench.make_config(name, wl)
+        assert set(bench.make_config(name, wl)) == {"workload", "seed", "l2", "inputs"}
+    fitted = {"cfg1": (3.11, 0.431, 34.6), "cfg2": (18.03, 0.102, 98.4), "cfg3": (8.81, 1.16, 67.4),
+              "cfg4": (12.13, 1.37, 82.3)}
+    for name, (e, p, lane) in fitted.items():
+        got = bench.fp64_lane_instr(1.0, {"executed_iters": e, "orbit_points": p})
+        assert abs(got - lane) / lane < 0.03, (name, got, lane)
