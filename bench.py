@@ -277,6 +277,13 @@ def reference_arm(args, wl, rank):
 # binning 4, at the orbit phase's lane occupancy).  Fit of the round-2 kernel: config 1 34.6
 # (model 34.6), config 2 98.4 (98.3), config 3 67.4 (66.3), config 4 82.3 (82.9) per candidate.
 FP64_MODEL = {"per_candidate": 17.0, "per_executed_iteration": 4.46, "per_orbit_point": 8.6}
+# All warp instructions the render kernel executes per unit of work (smsp__inst_executed of the same
+# captures: config 1 6.22, config 2 8.48, config 4 9.89 per candidate; the tiled config 3 runs 9 %
+# above the fit).  Used for the issue-port figure: on this machine an FP64 instruction holds a
+# sub-partition's issue port for two cycles and FP64-chain warps do not overlap with integer warps
+# (tools/mix_probe.cu, profiles/r02_issue_probes.txt), so
+#   cycles per candidate and sub-partition ~= warp instructions + FP64 warp instructions.
+INSTR_MODEL = {"per_candidate": 4.74, "per_executed_iteration": 0.196, "per_orbit_point": 2.02}
 HW_FP64_LANES = 148 * 64  # FP64 lanes of one B200: the hardware issue rate is this x the SM clock
 
 
@@ -293,6 +300,18 @@ def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload):
     lane = fp64_lane_instr(S, cnt, scale)
     lane_ref = 14 * S + 8 * cnt["escape_iters"] * scale + 8 * cnt["orbit_points"] * scale
     hw = HW_FP64_LANES * (sm_mhz or 1965.0) * 1e6
+    im = INSTR_MODEL
+    warp_instr = (im["per_candidate"] * S + im["per_executed_iteration"] * cnt["executed_iters"] * scale +
+                  im["per_orbit_point"] * cnt["orbit_points"] * scale)
+    port_cycles = warp_instr + lane / 32.0           # + one more cycle per FP64 warp instruction
+    avail_cycles = t_s * 148 * 4 * (sm_mhz or 1965.0) * 1e6
+    issue_port = {"frac": port_cycles / avail_cycles,
+                  "cycles_per_candidate_model": port_cycles / S,
+                  "cycles_per_candidate_measured": avail_cycles / S,
+                  "model": "issue-port cycles per candidate = warp instructions + FP64 warp "
+                           "instructions (an FP64 instruction holds a sub-partition's issue port "
+                           "for two cycles; FP64-chain and integer warps do not overlap: "
+                           "profiles/r02_issue_probes.txt), over 148 SM x 4 sub-partitions x SM clock"}
     return {
         "bound": "fp64-pipe", "unit": "Tlane-instr/s",
         "achieved": lane / t_s / 1e12, "peak": fp64_peak / 1e12, "frac": lane / t_s / fp64_peak,
@@ -310,6 +329,7 @@ def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload):
                      "bench.py FP64_MODEL)" % (FP64_MODEL["per_candidate"],
                                                 FP64_MODEL["per_executed_iteration"],
                                                 FP64_MODEL["per_orbit_point"]),
+        "issue_port": issue_port,
         "frac_reference_dataflow": lane_ref / t_s / fp64_peak,
         "reference_dataflow_note": "14 S + 8 E + 8 P with E = the iterations the REFERENCE must run "
                                    "for the same output (SURVEY.md 8(d)); a speed-up factor of the "
