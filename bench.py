@@ -616,7 +616,7 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
     return res
 
 
-def run_strong(cx, name="cfg3_m20000", n_total=1 << 38):
+def run_strong(cx, name="cfg3_m20000", n_total=1 << 39):
     """Strong scaling on the render north_star names for 8 GPUs: a FIXED range of n_total sample
     indices split contiguously over the ranks, one ncclReduce(sum) of the 1.6 GB histograms timed
     inside the job, and the digest of the merged histogram -- which must be the same for every
@@ -792,7 +792,7 @@ def main():
     ap.add_argument("--skip-baselines", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="only the headline workload: no strong-scaling job, no other workloads")
-    ap.add_argument("--strong-samples", type=int, default=1 << 38)
+    ap.add_argument("--strong-samples", type=int, default=1 << 39)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
