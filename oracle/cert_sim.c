@@ -1,13 +1,14 @@
 // Offline experiment (CPU, links oracle/liboracle.so; not part of the product): how many escape-pass iterations would a
 // contraction certificate save on never-escaping samples, compared with bit-exact detection?
 #include <stdio.h>
-// gcc -O2 -fopenmp -ffp-contract=off -mfma -o cert_sim cert_sim.c ../oracle/liboracle.so -lm -Wl,-rpath,$PWD/../oracle
+// (test infrastructure like the rest of oracle/: never linked or called by the product)
+// gcc -O2 -fopenmp -ffp-contract=off -mfma -o _ref/cert_sim cert_sim.c liboracle.so -lm -Wl,-rpath,$PWD
 // ./cert_sim 4194304 1e-5 0.9   ->  samples, tolerance of the near-return, multiplier bound
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <stdint.h>
-#include "../oracle/buddha_oracle.h"
+#include "buddha_oracle.h"
 static inline void step(double *re, double *im, double cr, double ci) {
   double t1 = *im * *im; double t2 = fma(*re, *re, -t1); double r2 = *re + *re;
   *im = fma(r2, *im, ci); *re = cr + t2;
