@@ -48,8 +48,14 @@ constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel wit
 constexpr int kDrainLong = 1024;                 // leftovers this long get a warp each, if they are few
 constexpr int kChunk = 4096;                   // granularity of launch sizes (host side)
 constexpr int kMinChunk = 1024, kMaxChunk = 16384;  // sample indices a warp takes per cursor grab
-constexpr int kT1End = 6;                      // the first exact tier covers steps 1 .. kT1End
-constexpr int kT2End = 22;                     // tier 2 covers steps kT1End+1 .. kT2End
+#ifndef BUDDHA_T1_END
+#define BUDDHA_T1_END 6
+#endif
+#ifndef BUDDHA_T2_END
+#define BUDDHA_T2_END 22
+#endif
+constexpr int kT1End = BUDDHA_T1_END;          // the first exact tier covers steps 1 .. kT1End
+constexpr int kT2End = BUDDHA_T2_END;          // tier 2 covers steps kT1End+1 .. kT2End
 constexpr int kLateSteps = 24;                 // per-step-tested steps per `late` batch
 constexpr int kBlock = 24;                     // unchecked steps per deep round (= kLateSteps)
 constexpr int kDeepExit = 31;                  // leave a phase when fewer lanes than this are busy
