@@ -251,17 +251,7 @@ struct Sink {
 __device__ __forceinline__ void scatter(const RenderParams &p, const Sink &k, uint32_t idx) {
   if (p.tile_shift) {
     uint2 *e = k.tile_tab + (idx >> p.tile_shift);
-#ifdef BUDDHA_MATCH_APPEND
-    // experiment: the lanes that append to the same tile take consecutive slots with ONE atomic,
-    // so their stores fall into the same sectors
-    const unsigned peers = __match_any_sync(__activemask(), idx >> p.tile_shift);
-    const int leader = __ffs(peers) - 1;
-    uint32_t slot = 0;
-    if ((int)lane_id() == leader) slot = atomicAdd(&e->x, (uint32_t)__popc(peers));
-    slot = __shfl_sync(peers, slot, leader) + __popc(peers & lanemask_lt());
-#else
     const uint32_t slot = atomicAdd(&e->x, 1u);
-#endif
     if (slot < e->y) {
       __stcs(p.pool + slot, idx & ((1u << p.tile_shift) - 1u));
       return;
