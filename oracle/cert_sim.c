@@ -17,6 +17,7 @@ static int cp_age(unsigned age) { unsigned rest = age & (age - 1u); return rest 
 int main(int argc, char **argv) {
   uint64_t n = argc > 1 ? strtoull(argv[1], 0, 0) : (1ull << 22);
   int maxit = 20000; double tol = argc > 2 ? atof(argv[2]) : 1e-5; double lam_max = argc > 3 ? atof(argv[3]) : 0.9;
+  const float p3_limit = argc > 4 ? (float)atof(argv[4]) : 0.96f;   // the kernel's period-3 bound on |lambda|^2
   double sum_exact = 0, sum_cert = 0, sum_cert_extra = 0; uint64_t inset = 0, exact_found = 0, cert_found = 0, p3 = 0, bad = 0;
 #pragma omp parallel for schedule(dynamic, 4096) reduction(+ : sum_exact, sum_cert, sum_cert_extra, inset, exact_found, cert_found, p3, bad)
   for (uint64_t s = 0; s < n; s++) {
@@ -26,7 +27,7 @@ int main(int argc, char **argv) {
     int it = oracle_escape_iterations(cr, ci, maxit);
     int escapes = it < maxit;
     if (it < 46) continue;
-    if (oracle_period3_flag(cr, ci, 0.96f)) { p3++; continue; }
+    if (oracle_period3_flag(cr, ci, p3_limit)) { p3++; continue; }
     // simulate deep rounds from step 46
     double re = cr, im = ci; for (int k = 0; k < 46; k++) step(&re, &im, cr, ci);
     double rre = re, rim = im; unsigned age = 0, age_cp = 0; int done = 46; int t_exact = -1, t_cert = -1, cert_cost = 0;

@@ -190,7 +190,7 @@ def blocked_fnv(hist):
     return int(out)
 
 
-def check_period3(seed, first, count, max_iter, limit=0.96):
+def check_period3(seed, first, count, max_iter, limit=0.998):
     """(flagged samples that escaped -- must be 0, flagged, all never-escaping samples): the evidence
     behind the kernel's conservative period-3 test (buddha_kernels.cuh: in_period3_component)."""
     L = lib()

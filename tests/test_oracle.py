@@ -194,7 +194,7 @@ def test_tonemap_max_pixel_quirk(oracle):
 
 def test_period3_component_test_is_conservative(oracle):
     """The kernel skips the escape loop for samples whose period-3 multiplier (closed form,
-    Giarrusso & Fisher) has |lambda|^2 < 0.96.  Every such sample must run the reference's loop
+    Giarrusso & Fisher) has |lambda|^2 < 0.998.  Every such sample must run the reference's loop
     (cudabrot.cu:319-340) to max_iterations; a limit beyond the component boundary (|lambda| = 1)
     must be caught by this very check."""
     for seed, first in ((1337, 0), (99, 1 << 40)):
