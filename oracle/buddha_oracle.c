@@ -596,8 +596,8 @@ uint64_t oracle_check_prefilter(uint64_t seed, uint64_t first, uint64_t count, i
   return bad;
 }
 
-/* A period-4 test of the same kind (derived and measured in round 2, not enabled in the kernel:
- * DESIGN.md section 5), in float: Newton
+/* The kernel's period-4 test (buddha_kernels.cuh: in_period4_component; used by the 80-register
+ * build) restated in float, two Newton steps like the kernel: Newton
  * from 0 on mu^3 - (3 - c^2) mu^2 + (3 + c^2 - c^3 - c^4) mu - (1 + 2c^2 + 3c^3 + 3c^4 + 3c^5 + c^6)
  * (mu = lambda / 16), accepted if |mu| + 3 |p / p'| < mu_max. */
 typedef struct { float r, i; } cfl;
@@ -616,7 +616,7 @@ int oracle_period4_flag(double c_real, double c_imag, float mu_max) {
   const cfl a0 = {-(1.0f + 2.0f * c2.r + 3.0f * (c3.r + c4.r + c5.r) + c6.r),
                   -(2.0f * c2.i + 3.0f * (c3.i + c4.i + c5.i) + c6.i)};
   cfl mu = {0.0f, 0.0f}, p = a0, dp = a1;
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < 2; k++) {
     const cfl q = cfl_div(p, dp);
     mu.r -= q.r; mu.i -= q.i;
     p = cfl_add(cfl_mul(cfl_add(cfl_mul(cfl_add(mu, a2), mu), a1), mu), a0);

@@ -141,8 +141,7 @@ int oracle_prefilter_class(uint32_t hi_re, uint32_t hi_im, int ship, float m_rej
 uint64_t oracle_check_prefilter(uint64_t seed, uint64_t first, uint64_t count, int ship,
                                 float m_rej, float m_esc, uint64_t counts[4]);
 
-/* The same pair for a period-4 test (Newton for a small root of the multiplier cubic); not enabled
- * in the kernel, kept as the evidence for the cubic quoted in DESIGN.md. */
+/* The same pair for the period-4 test (Newton for a small root of the multiplier cubic). */
 int oracle_period4_flag(double c_real, double c_imag, float mu_max);
 uint64_t oracle_check_period4(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
                               float mu_max, uint64_t *flagged, uint64_t *inset);

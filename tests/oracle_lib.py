@@ -202,9 +202,8 @@ def check_period3(seed, first, count, max_iter, limit=0.998):
     return int(bad), fl.value, ins.value
 
 
-def check_period4(seed, first, count, max_iter, mu_max=0.98 / 16):
-    """Like check_period3 for the period-4 multiplier cubic (not enabled in the
-    kernel)."""
+def check_period4(seed, first, count, max_iter, mu_max=0.999 / 16):
+    """Like check_period3 for the period-4 test (buddha_kernels.cuh: in_period4_component)."""
     L = lib()
     L.oracle_check_period4.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_float,
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]

@@ -220,15 +220,13 @@ def test_sampler_prefilter_is_conservative(oracle):
 
 
 def test_period4_component_test_is_conservative(oracle):
-    """The period-4 multiplier cubic derived for DESIGN.md section 5 (a kernel test built on it was
-    measured and not kept: it removes 6.5 % of the executed iterations but its own cost eats the
-    gain).  The same evidence as for period 3: Newton for a root of the multiplier cubic
-    mu^3 - (3 - c^2) mu^2 + (3 + c^2 - c^3 - c^4) mu - (1 + 2c^2 + 3c^3 + 3c^4 + 3c^5 + c^6), mu =
-    lambda / 16, accepted when |mu| + 3 |p / p'| < 0.98 / 16.  Every flagged sample must run the
-    reference's loop to max_iterations; a bound beyond |lambda| = 1 must be caught."""
+    """Same evidence for the period-4 test of the 80-register build: Newton for a small root of the
+    multiplier cubic mu^3 - (3 - c^2) mu^2 + (3 + c^2 - c^3 - c^4) mu - (1 + 2c^2 + 3c^3 + 3c^4 + 3c^5
+    + c^6), mu = lambda / 16, accepted when |mu| + 3 |p / p'| < 0.999 / 16.  Every flagged sample
+    must run the reference's loop to max_iterations; a bound beyond |lambda| = 1 must be caught."""
     for seed, first in ((1337, 0), (99, 1 << 40)):
         bad, flagged, inset = oracle.check_period4(seed, first, 1 << 22, 20000)
         assert bad == 0
-        assert 0.13 < flagged / inset < 0.21          # period-4 components: ~17 % of what is left
+        assert 0.13 < flagged / inset < 0.21          # period-4 components: ~17.5 % of what is left
     bad, _, _ = oracle.check_period4(1337, 0, 1 << 22, 20000, mu_max=1.05 / 16)
     assert bad > 0
