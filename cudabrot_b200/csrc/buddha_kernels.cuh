@@ -42,6 +42,14 @@ constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 // because every phase that pushes to them starts only while late + orb <= kZJoint (else `late`
 // runs first, with whatever it holds).
 constexpr int kDeepCap = 63;
+// Attracting-cycle certificate (cert_phase): its candidates wait in the deep arrays, growing down
+// from the top; deep + cert <= kDeepArr because `late` pushes to deep only while both fit with 32
+// to spare, and every other push moves entries that were already counted.
+constexpr int kDeepArr = kDeepCap + 16;
+#ifndef BUDDHA_CERT_RUN
+#define BUDDHA_CERT_RUN 24
+#endif
+constexpr int kCertRun = BUDDHA_CERT_RUN;      // the certificate runs on batches of at least this many
 constexpr int kZCap = 87, kZJoint = kZCap - 32;
 constexpr int kCCap = 94;
 constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel with < 32 accepted samples
@@ -455,14 +463,15 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 //   z_*      late (0 up): it = iterations done; orb (kZCap-1 down): it = steps still to record
 //   deep_*   carry their checkpoint, so suspending a lane does not restart the periodicity search
 //            (long cycles need long uninterrupted windows); meta = (last, age): the age after which
-//            no further full round fits below max_it, and the rounds spent in deep so far
+//            no further full round fits below max_it, and the rounds spent in deep so far.
+//            cert (slots kDeepArr-1 down, no deep_r): samples waiting for the cycle certificate
 struct WarpQueues {
-  double2 deep_c[kDeepCap], deep_z[kDeepCap], deep_r[kDeepCap];
+  double2 deep_c[kDeepArr], deep_z[kDeepArr], deep_r[kDeepCap];
   double2 z_c[kZCap], z_z[kZCap];
   union { double2 c_c[kCCap]; uint4 c_w[kCCap]; };
-  uint2 deep_meta[kDeepCap];
+  uint2 deep_meta[kDeepArr];
   int z_it[kZCap];
-  int pad[(4 - (2 * kDeepCap + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
+  int pad[(4 - (2 * kDeepArr + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
   // fused render: this warp's per-channel / per-band accumulators (ChannelSlot), added to the
   // global ones when the kernel ends.  (They used to be global atomics from every late / tier
   // batch: 6 same-address atomics per ~1000 candidates from 10 000 warps.)
@@ -478,7 +487,7 @@ constexpr bool kT0 = false, kT2 = true;     // the two stacks in c_*
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
-  int t0_n, t2_n, late_n, deep_n, orb_n;  // stack heights (warp-uniform)
+  int t0_n, t2_n, late_n, deep_n, orb_n, cert_n;  // stack heights (warp-uniform)
   unsigned long long chunk_base;           // first sample index of the chunk this warp owns
   uint32_t chunk_off, chunk_len;           // progress inside the chunk
   bool exhausted;                          // the global cursor ran past p.end
@@ -828,7 +837,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
     cx = c.x; cy = c.y; x = z.x; y = z.y; it = q.z_it[slot];
   }
   __syncwarp();  // the slots are re-used by the pushes below
-  const bool deep_room = ws.deep_n < 32;
+  const bool deep_room = ws.deep_n < 32 && ws.deep_n + ws.cert_n <= kDeepArr - 32;
   bool alive = act;
   int cnt = 0;
   tested_steps<kVar, kLateSteps>(x, y, cx, cy, alive, cnt);
@@ -864,6 +873,42 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
   __syncwarp();
 }
 
+// ---- attracting-cycle certificate ---------------------------------------------------------------
+//
+// After the closed-form tests for periods 3 and 4 the never-escaping samples that are left (0.33 %
+// of the candidates on config 2) still cost 10.5 of the 14.1 iterations a candidate executes: they
+// run until their state repeats bit for bit, 3160 iterations on average.  A sample that has spent
+// 4, 16, 64, ... rounds in `deep` is therefore handed to cert_phase, which looks for the attracting
+// cycle itself, lane-parallel on a batch of such samples:
+//   1. period: the first k <= pmax with |z_k - z| < kCertTol, iterating in float from the sample's
+//      current state z;
+//   2. Newton on f^p(w) - w in double from w = z, the derivative d = prod 2 w_j carried along the
+//      p steps (on the scaled state 2 w = X + iY, so d <- (X + iY) d: four FP64 instructions);
+//   3. accepted if the residual |f^p(w) - w| is below kCertResMax and |d|^2 < kCertLam2Max.
+// Then f_c has an attracting cycle.  A quadratic polynomial has at most one attracting cycle and it
+// attracts the critical orbit (Fatou), so c lies in a hyperbolic component of the Mandelbrot set,
+// the orbit of 0 converges to the cycle, and the reference's loop runs to max_iterations whatever
+// that is: `hit max` without iterating further.  Histogram-neutral like the periodicity check and
+// the period-3/4 tests, and evidence of the same kind: the test suite restates it on the CPU
+// (check_certificate) and runs the reference's own loop on every certified sample (0 escapes among 425 000
+// certified in 2 x 2^26 samples; with the multiplier bound at 1.1 the same check finds 195 in 2^22),
+// and every GPU parity test runs with it (and without: BUDDHA_F_NO_SHORTCUT).  Samples the certificate cannot settle
+// (period > pmax, multiplier too close to 1, Newton not converged) go back to `deep` unchanged.
+// On config 2 it settles 96 % of the remaining never-escaping samples, 588 instead of 3160
+// iterations each.
+constexpr unsigned kCertFirstAge = 4;            // tried at ages 4, 16, 64, ... (powers of four)
+constexpr int kCertPmaxFirst = 32, kCertPmaxLater = 64;
+constexpr int kCertPasses = 5;                   // Newton evaluations (the last one only verifies)
+constexpr float kCertTol = 1e-2f;
+constexpr double kCertResMax = 1e-12, kCertLam2Max = 0.998;
+constexpr int kCertMinIt = 4000;                 // below this -m the bit-exact search is cheaper
+
+// the next age at which a sample of age `age` is due for the certificate: the smallest power of
+// four >= kCertFirstAge that is > age
+__device__ __forceinline__ unsigned next_cert_age(unsigned age) {
+  return 1u << (((31 - __clz((int)(age | 1u))) & ~1) + 2);
+}
+
 // Checkpoint schedule of the periodicity search: a new checkpoint after 1, 2, 3, 4, 6, 8, 12, 16,
 // 24, ... rounds (ages with at most two significant bits).  A cycle is found once a checkpoint
 // lies on it and the gap to the next checkpoint covers its period (in rounds); the 1.33..1.5
@@ -886,17 +931,19 @@ __device__ __forceinline__ bool checkpoint_age(unsigned age) {
 // per sample), so it is kept short: no per-lane iteration counters (see WarpState::d_rounds), and
 // finished lanes keep iterating on stale values, which nothing reads (`act` guards every use; a
 // stale orbit may run to inf/NaN, which costs nothing on this hardware).
-template <int kVar>
+template <int kVar, bool kCert>
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                            bool drain, unsigned long long *counters) {
   static_assert(kLateSteps == kBlock, "late batches and deep rounds must have the same length");
   const int max_it = p.max_it;
   const int m24 = max_it - (max_it - kT2End) % kBlock;
   const bool shortcut = p.shortcut != 0;
+  const bool cert_on = kCert && shortcut && max_it >= kCertMinIt;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
   unsigned age = 0;     // rounds this sample has spent in deep (checkpoint schedule)
   unsigned last = 0;    // the age after which no further full round fits below max_it
+  unsigned ev = 0;      // the next age at which the lane needs attention: min(last, certificate age)
 #pragma unroll 1
   for (;;) {
     // keep room for 32 hand-backs
@@ -910,6 +957,7 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
         const uint2 meta = q.deep_meta[slot];
         cx = c.x; cy = c.y; x = z.x; y = z.y; rx = r.x; ry = r.y;
         last = meta.x; age = meta.y;  // last >= age + 1
+        ev = cert_on ? min(last, next_cert_age(age)) : last;
         ws.d_rounds -= (int32_t)age;
         act = true;
       }
@@ -934,7 +982,7 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       out = !(norm4(x, y) <= 16.0);  // also true for NaN / inf
       age++;
       same_x = shortcut && __double_as_longlong(x) == __double_as_longlong(rx);
-    } while (__ballot_sync(kFull, act && (out || same_x || age == last)) == 0u);
+    } while (__ballot_sync(kFull, act && (out || same_x || age == ev)) == 0u);
     {
       // (the copy hides `age` from the compiler's induction-variable pass, which otherwise keeps
       // `it` and last - age up to date inside the round loop: eight extra adds per round)
@@ -954,12 +1002,110 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
       if (__ballot_sync(kFull, back))
         push_z<kLate>(q, ws.late_n, back, cx, cy, out ? x0 : x, out ? y0 : y, out ? it - kBlock : it);
       act = act && !fin;
+      if constexpr (kCert) {
+        // due for the cycle certificate: suspended onto the cert stack (top of the deep arrays)
+        const bool due = act && cert_on && age_now == ev;
+        const unsigned dm = __ballot_sync(kFull, due);
+        if (dm) {
+          const int slot = kDeepArr - 1 - (ws.cert_n + __popc(dm & lanemask_lt()));
+          ws.cert_n += __popc(dm);
+          if (due) {
+            q.deep_c[slot] = make_double2(cx, cy); q.deep_z[slot] = make_double2(x, y);
+            q.deep_meta[slot] = make_uint2(last, age_now);
+          }
+          ws.d_rounds += due ? (int32_t)age_now : 0;
+          act = act && !due;
+        }
+      }
       // with a very large -m a few never-escaping samples could wrap the 32-bit counter
       if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);
     }
   }
   ws.d_rounds += act ? (int32_t)age : 0;
   push_deep(q, ws, act, cx, cy, x, y, rx, ry, last, age);  // keeps the checkpoint and its schedule
+  __syncwarp();
+}
+
+// (c') the cycle certificate on a batch of up to 32 suspended deep samples (see above).  Certified
+// samples are `hit max`; the others return to `deep` with their state, age and schedule (the
+// checkpoint restarts at the current state: every certificate age is a checkpoint age anyway).
+template <int kVar>
+__device__ __forceinline__ void cert_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                           unsigned long long *counters) {
+  const int take = min(ws.cert_n, 32);
+  const bool act = (int)lane_id() < take;
+  ws.cert_n -= take;
+  double cx = 0.0, cy = 0.0, zx = 0.0, zy = 0.0;
+  unsigned last = 0, age = 0;
+  if (act) {
+    const int slot = kDeepArr - 1 - (ws.cert_n + (int)lane_id());
+    const double2 c = q.deep_c[slot], z = q.deep_z[slot];
+    const uint2 meta = q.deep_meta[slot];
+    cx = c.x; cy = c.y; zx = z.x; zy = z.y; last = meta.x; age = meta.y;
+  }
+  __syncwarp();
+  const double x_in = zx, y_in = zy;
+  // 1. period search in float
+  const int pmax = act ? (age == kCertFirstAge ? kCertPmaxFirst : kCertPmaxLater) : 0;
+  int per = 0;
+  {
+    const float fcx = (float)cx, fcy = (float)cy, fx0 = (float)zx, fy0 = (float)zy;
+    const float tol2 = 4.0f * kCertTol * kCertTol;   // scaled state: distances are doubled
+    float fx = fx0, fy = fy0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < kCertPmaxLater; k0 += 8) {
+#pragma unroll
+      for (int j = 1; j <= 8; j++) {
+        const float a4 = fy * fy, b4 = __fmaf_rn(fx, fx, -a4), yn = __fmaf_rn(fx, fy, fcy);
+        fx = __fmaf_rn(b4, 0.5f, fcx); fy = yn;
+        const float dx = fx - fx0, dy = fy - fy0;
+        if (per == 0 && __fmaf_rn(dy, dy, dx * dx) < tol2) per = k0 + j;
+      }
+      if (__all_sync(kFull, per != 0 || k0 + 8 >= pmax)) break;
+    }
+    if (per > pmax) per = 0;
+  }
+  // 2. Newton on f^per(w) - w, all lanes in lockstep over the longest period of the batch
+  const int maxp = __reduce_max_sync(kFull, per);
+  double rx = 1.0, ry = 1.0, dr = 1.0, di = 0.0;   // residual (scaled) and multiplier at the last iterate
+  const double res2_max = kCertResMax * kCertResMax;
+  if (maxp > 0) {
+#pragma unroll 1
+    for (int pass = 0; pass < kCertPasses; pass++) {
+      double x = zx, y = zy;
+      dr = 1.0; di = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < maxp; k++) {
+        if (k < per) {
+          const double ndr = __fma_rn(x, dr, -__dmul_rn(y, di)), ndi = __fma_rn(x, di, __dmul_rn(y, dr));
+          dr = ndr; di = ndi;
+          zstep<false>(x, y, cx, cy);
+        }
+      }
+      rx = __dsub_rn(x, zx); ry = __dsub_rn(y, zy);
+      const bool conv = __fma_rn(ry, ry, __dmul_rn(rx, rx)) < res2_max;
+      if (pass + 1 == kCertPasses || __all_sync(kFull, per == 0 || conv)) break;
+      const double er = __dsub_rn(dr, 1.0), ei = di;
+      // (an approximate reciprocal is enough: a slightly inexact Newton step still contracts)
+      const double inv = (double)__frcp_rn((float)__fma_rn(er, er, __dmul_rn(ei, ei)));
+      // w <- w - r / (d - 1) = w - r conj(d - 1) / |d - 1|^2
+      zx = __dsub_rn(zx, __dmul_rn(__fma_rn(rx, er, __dmul_rn(ry, ei)), inv));
+      zy = __dsub_rn(zy, __dmul_rn(__fma_rn(ry, er, -__dmul_rn(rx, ei)), inv));
+    }
+  }
+  // 3. certified: an attracting cycle (NaN compares false)
+  const bool ok = act && per > 0 && __fma_rn(ry, ry, __dmul_rn(rx, rx)) < res2_max &&
+                  __fma_rn(di, di, __dmul_rn(dr, dr)) < kCertLam2Max;
+  {
+    const int max_it = p.max_it;
+    const int m24 = max_it - (max_it - kT2End) % kBlock;
+    const int it = m24 - (int)(last - age) * kBlock;   // iterations the sample has done
+    ws.n_hit += ok ? 1u : 0u;
+    ws.n_cyc += ok ? 1u : 0u;
+    ws.skipped += ok ? (uint32_t)(max_it - it) : 0u;
+  }
+  push_deep(q, ws, act && !ok, cx, cy, x_in, y_in, x_in, y_in, last, age);
+  if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);  // (huge -m)
   __syncwarp();
 }
 
@@ -1111,7 +1257,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     __syncwarp();
   }
   WarpState ws;
-  ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = 0;
+  ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = ws.cert_n = 0;
   if (spill.carry_in) {  // the orbits this warp parked at the end of the previous launch
     // (the broadcast tells the compiler the count is warp-uniform: without it every vote in the
     //  scheduler loop below is compiled with a divergence fallback, +40 % code, -5 % speed)
@@ -1135,6 +1281,8 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
+  // (the certificate, like the period-4 test, only pays in the plain 80-register build so far)
+  constexpr bool kCertBuild = kVar == 0 && kMaxReg == kRegsWide;
 #pragma unroll 1
   for (;;) {
     // strict priority along the push graph: a phase is reached only when every stack it pushes
@@ -1147,7 +1295,13 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     } else if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint || (dry2 && ws.late_n > 0)) {
       late_phase<kVar, (kMaxReg == kRegsWide) && (kVar & kVarFused) == 0>(p, q, ws, counters);
     } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
-      deep_phase<kVar>(p, q, ws, dry3, counters);
+      deep_phase<kVar, kCertBuild>(p, q, ws, dry3, counters);
+    } else if (kCertBuild &&
+               (ws.cert_n >= kCertRun ||
+                (ws.cert_n > 0 && (dry3 || ws.deep_n + ws.cert_n > kDeepArr - 32)))) {
+      // (the last condition: `late` may not push to deep while the shared arrays are this full,
+      //  and deep itself holds < 32 here, so the waiting certificates have to make room)
+      cert_phase<kVar>(p, q, ws, counters);
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
       tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, ws.t2_n, counters);
     } else if (ws.t0_n >= 32 || (dry && ws.t0_n > 0)) {

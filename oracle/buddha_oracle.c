@@ -649,3 +649,111 @@ uint64_t oracle_check_period4(uint64_t seed, uint64_t first, uint64_t count, int
   if (inset) *inset = in;
   return bad;
 }
+
+/* ---- attracting-cycle certificate (buddha_kernels.cuh: cert_phase) ----------------------------
+ * Restated on the scaled state (X = 2 re, Y = 2 im) like the kernel:
+ *   1. period search in float: the first k <= pmax with |z_k - z_0| < tol (scaled: 2 tol);
+ *   2. `passes` Newton steps on f^p(z) - z in double, the derivative d = prod 2 z_j carried along
+ *      (on the scaled state 2 z = X + iY, so d <- (X + iY) d); the reciprocal of |d - 1|^2 is
+ *      taken in float (a slightly inexact Newton step still contracts);
+ *   3. at the last iterate: residual |f^p(z) - z| (scaled) below res_max and |d|^2 < lam2_max.
+ * f_c then has an attracting cycle; a quadratic polynomial has at most one, and it attracts the
+ * critical orbit (Fatou), so c lies in a hyperbolic component and the orbit of 0 never escapes.
+ * Returns the period, or 0 if no certificate was obtained. */
+int oracle_cycle_certificate(double c_real, double c_imag, double z_real, double z_imag, int pmax,
+                             float tol, int passes, double res_max, double lam2_max) {
+  const double cx = 2.0 * c_real, cy = 2.0 * c_imag;
+  double zx = 2.0 * z_real, zy = 2.0 * z_imag;
+  const float fcx = (float)cx, fcy = (float)cy, fx0 = (float)zx, fy0 = (float)zy;
+  float fx = fx0, fy = fy0;
+  const float tol2 = 4.0f * tol * tol;
+  int p = 0;
+  for (int k = 1; k <= pmax; k++) {
+    const float a4 = fy * fy, b4 = fmaf(fx, fx, -a4), yn = fmaf(fx, fy, fcy);
+    fx = fmaf(b4, 0.5f, fcx); fy = yn;
+    const float dx = fx - fx0, dy = fy - fy0;
+    if (fmaf(dy, dy, dx * dx) < tol2) { p = k; break; }
+  }
+  if (!p) return 0;
+  double rx = 0.0, ry = 0.0, dr = 1.0, di = 0.0;
+  for (int pass = 0; pass < passes; pass++) {
+    double x = zx, y = zy;
+    dr = 1.0; di = 0.0;
+    for (int k = 0; k < p; k++) {
+      const double ndr = FMA(x, dr, -(y * di)), ndi = FMA(x, di, y * dr);
+      dr = ndr; di = ndi;
+      const double a4 = y * y, b4 = FMA(x, x, -a4), yn = FMA(x, y, cy);
+      x = FMA(b4, 0.5, cx); y = yn;
+    }
+    rx = x - zx; ry = y - zy;                      /* scaled residual */
+    if (pass + 1 == passes) break;
+    const double er = dr - 1.0, ei = di;
+    const double inv = (double)(1.0f / (float)FMA(er, er, ei * ei));
+    /* z <- z - r / (d - 1) = z - r conj(d - 1) / |d - 1|^2 */
+    zx -= FMA(rx, er, ry * ei) * inv;
+    zy -= FMA(ry, er, -(rx * ei)) * inv;
+  }
+  if (!(FMA(ry, ry, rx * rx) < res_max * res_max)) return 0;
+  if (!(FMA(di, di, dr * dr) < lam2_max)) return 0;
+  return p;
+}
+
+/* Evidence for the certificate, in the setting the kernel uses it: samples that survive
+ * 46 steps enter rounds of 24 unchecked steps; at ages (rounds) trig0, trig0 * trig_mul, ... the
+ * certificate is tried (pmax1 at the first age, pmax2 later; the kernel: 4, 16, 64, ...).  Returns the number of certified samples that ESCAPE
+ * under the reference's loop within max_iterations (must be 0).  stats[0] = candidates not
+ * rejected, [1] = never-escaping samples not flagged by the period-3/4 tests, [2] = certified among
+ * them, [3] = their iterations with bit-exact detection only, [4] = with the certificate,
+ * [5] = certificate attempts, [6] = sum over attempts of (pmax searched), [7] = sum over
+ * attempts that found a period of that period. */
+uint64_t oracle_check_certificate(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                                  int trig0, int trig_mul, int pmax1, int pmax2, float tol, int passes, double res_max,
+                                  double lam2_max, uint64_t stats[8]) {
+  uint64_t bad = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : bad, s0, s1, s2, s3, s4, s5, s6, s7)
+#endif
+  for (uint64_t k = 0; k < count; k++) {
+    double cre, cim;
+    oracle_sample(seed, first + k, &cre, &cim);
+    if (oracle_rejected(cre, cim)) continue;
+    s0++;
+    const int it = oracle_escape_iterations(cre, cim, max_iterations);
+    if (it < 46) continue;
+    if (oracle_period3_flag(cre, cim, 0.998f) || oracle_period4_flag(cre, cim, 0.999f / 16.0f)) continue;
+    double re = cre, im = cim;
+    for (int j = 0; j < 46; j++) {
+      double t1 = im * im, t2 = FMA(re, re, -t1), r2 = re + re;
+      im = FMA(r2, im, cim); re = cre + t2;
+    }
+    double rre = re, rim = im;
+    unsigned age = 0, trig = (unsigned)trig0;
+    int done = 46, t_exact = -1, t_cert = -1;
+    while (done + 24 <= max_iterations) {
+      if (age == trig) {
+        trig *= (unsigned)trig_mul;
+        if (t_cert < 0) {
+          const int pm = age == (unsigned)trig0 ? pmax1 : pmax2;
+          const int p = oracle_cycle_certificate(cre, cim, re, im, pm, tol, passes, res_max, lam2_max);
+          s5++; s6 += (uint64_t)pm; s7 += (uint64_t)p;
+          if (p) t_cert = done;
+        }
+      }
+      { const unsigned rest = age & (age - 1u); if (rest == 0u || 3u * rest == 2u * age) { rre = re; rim = im; } }
+      for (int j = 0; j < 24; j++) {
+        double t1 = im * im, t2 = FMA(re, re, -t1), r2 = re + re;
+        im = FMA(r2, im, cim); re = cre + t2;
+      }
+      done += 24; age++;
+      if (!(FMA(im, im, re * re) <= 4.0)) break;
+      if (memcmp(&re, &rre, 8) == 0 && memcmp(&im, &rim, 8) == 0) { t_exact = done; break; }
+    }
+    if (it < max_iterations) { if (t_cert >= 0) bad++; continue; }
+    s1++;
+    const int te = t_exact >= 0 ? t_exact : max_iterations;
+    s3 += (uint64_t)te;
+    if (t_cert >= 0) { s2++; s4 += (uint64_t)t_cert; } else s4 += (uint64_t)te;
+  }
+  if (stats) { stats[0] = s0; stats[1] = s1; stats[2] = s2; stats[3] = s3; stats[4] = s4; stats[5] = s5; stats[6] = s6; stats[7] = s7; }
+  return bad;
+}

@@ -146,6 +146,17 @@ int oracle_period4_flag(double c_real, double c_imag, float mu_max);
 uint64_t oracle_check_period4(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
                               float mu_max, uint64_t *flagged, uint64_t *inset);
 
+/* The kernel's attracting-cycle certificate (buddha_kernels.cuh: cert_phase) restated: float period
+ * search from the state z, Newton on f^p(z) - z in double, accepted if the residual and the
+ * multiplier are small.  Returns the period or 0.  oracle_check_certificate tries it where the
+ * kernel does (deep ages 4, 16, 64, ...) and returns how many certified samples escape under the
+ * reference's loop (must be 0); stats[8] is described at the definition. */
+int oracle_cycle_certificate(double c_real, double c_imag, double z_real, double z_imag, int pmax,
+                             float tol, int passes, double res_max, double lam2_max);
+uint64_t oracle_check_certificate(uint64_t seed, uint64_t first, uint64_t count, int max_iterations,
+                                  int trig0, int trig_mul, int pmax1, int pmax2, float tol, int passes, double res_max,
+                                  double lam2_max, uint64_t stats[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,6 +213,26 @@ def check_period4(seed, first, count, max_iter, mu_max=0.999 / 16):
     return int(bad), fl.value, ins.value
 
 
+def check_certificate(seed, first, count, max_iter, lam2_max=0.998, pmax=(32, 64), tol=1e-2, passes=5,
+                      res_max=1e-12, first_age=4, age_factor=4):
+    """(certified samples that escaped -- must be 0, stats): the evidence behind the kernel's
+    attracting-cycle certificate (buddha_kernels.cuh: cert_phase), tried where the kernel tries it.
+    stats: not_rejected, inset (never-escaping, not flagged by the period-3/4 tests), certified,
+    iterations of the inset samples with the bit-exact search only / with the certificate,
+    attempts."""
+    L = lib()
+    L.oracle_check_certificate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_float, C.c_int, C.c_double,
+                                           C.c_double, C.POINTER(C.c_uint64)]
+    L.oracle_check_certificate.restype = C.c_uint64
+    st = (C.c_uint64 * 8)()
+    bad = L.oracle_check_certificate(seed, first, count, max_iter, first_age, age_factor, pmax[0],
+                                     pmax[1], tol, passes, res_max, lam2_max, st)
+    keys = ("not_rejected", "inset", "certified", "iters_exact", "iters_cert", "attempts",
+            "searched", "periods")
+    return int(bad), {k: int(v) for k, v in zip(keys, st)}
+
+
 def check_prefilter(seed, first, count, ship=False, m_rej=0.02, m_esc=0.05):
     """(decided samples that disagree with the reference's arithmetic -- must be 0, [undecided,
     rejected, escapes at step 1, at step 2]): the evidence behind the sampler's FP32

@@ -230,3 +230,18 @@ def test_period4_component_test_is_conservative(oracle):
         assert 0.13 < flagged / inset < 0.21          # period-4 components: ~17.5 % of what is left
     bad, _, _ = oracle.check_period4(1337, 0, 1 << 22, 20000, mu_max=1.05 / 16)
     assert bad > 0
+
+
+def test_cycle_certificate_is_conservative(oracle):
+    """The kernel declares a sample `hit max` once it has found an attracting cycle of z^2 + c
+    (period search in float, Newton in double, residual < 1e-12, |multiplier|^2 < 0.998): c then lies
+    in a hyperbolic component.  Every certified sample must run the reference's loop
+    (cudabrot.cu:319-340) to max_iterations; a multiplier bound beyond 1 must be caught by this very
+    check.  The certificate has to settle most of what the closed-form period-3/4 tests leave."""
+    for seed, first in ((1337, 0), (99, 1 << 40)):
+        bad, st = oracle.check_certificate(seed, first, 1 << 22, 20000)
+        assert bad == 0
+        assert st["certified"] > 0.93 * st["inset"]
+        assert st["iters_cert"] < 0.25 * st["iters_exact"]
+    bad, _ = oracle.check_certificate(1337, 0, 1 << 22, 20000, lam2_max=1.1)
+    assert bad > 0
