@@ -69,7 +69,9 @@ CHANNELS = {"cfg5": [(100, 20), (1000, 20), (20000, 20)],
 REFERENCE_PASS = 13107200  # 512 blocks * 512 threads * 50 samples, cudabrot.cu:20,23,34
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_persistent_kernel launch over 2^30
 # samples, from the `ncu --set full` captures summarised in profiles/r02_summary.md
-NCU_DRAM_BYTES_PER_2P30_LAUNCH = {"cfg1": 4038912 + 5376, "cfg2": 39680 + 0,
+# (config 2: 40 KB before the cycle certificate; its queues -- 48 B per parked sample, 0.17 % of the
+#  candidates -- are the 80 MB now: a quarter of the 2^32-sample capture r02_render_cfg2_cert_*)
+NCU_DRAM_BYTES_PER_2P30_LAUNCH = {"cfg1": 4038912 + 5376, "cfg2": (16600320 + 304296704) // 4,
                                   "cfg3": 255045120 + 5058764000, "cfg4": 127435520 + 2082458000}
 METRIC = "candidate samples/sec"
 

@@ -63,6 +63,8 @@ struct buddha_ctx {
   unsigned long long *d_counters; // kCntSlots accumulators
   OrbitSpill spill[2];            // grid-wide lists of orbits left over by the render kernel
   unsigned int *d_spill_next[2];  // (two: the drain of launch k overlaps the render of launch k+1)
+  double2 *d_cert_c, *d_cert_z;   // certificate queues (cert_phase in buddha_kernels.cuh), kCertQueue
+  uint4 *d_cert_m;                // entries per warp of the render grid; only where the build uses them
   // tile-binned scatter (histograms far beyond L2), see scatter() in buddha_kernels.cuh
   bool tiled, tile_calibrated;
   int tile_shift, n_tiles;
@@ -398,7 +400,19 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
                                (const void *)render_persistent_kernel<1, kRegsLean>,
                                (const void *)render_persistent_kernel<2, kRegsLean>,
                                (const void *)render_persistent_kernel<3, kRegsLean>};
-  const void *render_fn = render_fns[c->variant + (c->tiled ? 4 : 0)];
+  // The cycle certificate (cert_phase in buddha_kernels.cuh): plain render (not fused, not burning
+  // ship) in the 80-register build, shortcuts allowed, and -m large enough for the saved iterations
+  // to outweigh the certificate.  A separate instantiation of the kernel.
+  size_t cert_cap = 0;
+  if (c->variant == 0 && !c->tiled &&
+      !(p->flags & (BUDDHA_F_SIMPLE_KERNEL | BUDDHA_F_NO_SHORTCUT)) &&
+      p->max_iterations >= kCertMinIt) {
+    cert_cap = kCertQueue;
+    if (const char *e = getenv("BUDDHA_CERT_QUEUE")) cert_cap = (size_t)strtoull(e, nullptr, 10);  // A/B runs; 0 = off
+    if (cert_cap < 2 * kCertHeadroom + 96) cert_cap = 0;
+  }
+  const void *render_fn = cert_cap ? (const void *)render_persistent_kernel<0, kRegsWide, true>
+                                   : render_fns[c->variant + (c->tiled ? 4 : 0)];
   cudaFuncAttributes fattr;
   cudaError_t st = cudaFuncGetAttributes(&fattr, render_fn);
   if (st == cudaSuccess)
@@ -513,6 +527,14 @@ int buddha_create(buddha_ctx **out, const buddha_params *p) {
       c->rp.pool = c->d_pool;
     }
   }
+  if (cert_cap) {   // the certificate queues: cert_cap entries per warp of the render grid
+    const size_t entries = (size_t)c->grid * kWarpsPerCta * cert_cap;
+    CUC(cudaMalloc(&c->d_cert_c, sizeof(double2) * entries));
+    CUC(cudaMalloc(&c->d_cert_z, sizeof(double2) * entries));
+    CUC(cudaMalloc(&c->d_cert_m, sizeof(uint4) * entries));
+    c->rp.cert_c = c->d_cert_c; c->rp.cert_z = c->d_cert_z; c->rp.cert_m = c->d_cert_m;
+    c->rp.cert_cap = (uint32_t)cert_cap;
+  }
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
@@ -534,6 +556,7 @@ void buddha_destroy(buddha_ctx *c) {
   if (c->ev_applied[0]) cudaEventDestroy(c->ev_applied[0]);
   if (c->ev_applied[1]) cudaEventDestroy(c->ev_applied[1]);
   cudaFree(c->d_pool); cudaFree(c->d_tcount); cudaFree(c->d_tcap); cudaFree(c->d_tbase);
+  cudaFree(c->d_cert_c); cudaFree(c->d_cert_z); cudaFree(c->d_cert_m);
   for (int k = 0; k < 2; k++) {
     cudaFree(c->tone[k].d_max); cudaFree(c->tone[k].d_gray); cudaFree(c->tone[k].d_lut);
     cudaFree(c->tone[k].d_thr); cudaFree(c->tone[k].d_chan);
@@ -729,7 +752,10 @@ static int launch_render(buddha_ctx *c, uint64_t first, uint64_t count, bool car
     default: render_persistent_kernel<3, REGS><<<grid, kThreadsPerCta, rsmem, c->stream>>>( \
         rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]); break;                     \
   }
-    if (c->tiled) { BUDDHA_LAUNCH_RENDER(kRegsLean) } else { BUDDHA_LAUNCH_RENDER(kRegsWide) }
+    if (rp.cert_cap != 0u) {   // plain render, 80-register build, with the cycle certificate
+      render_persistent_kernel<0, kRegsWide, true><<<grid, kThreadsPerCta, rsmem, c->stream>>>(
+          rp, c->d_hist, c->d_cursor, c->d_counters, c->spill[b]);
+    } else if (c->tiled) { BUDDHA_LAUNCH_RENDER(kRegsLean) } else { BUDDHA_LAUNCH_RENDER(kRegsWide) }
     CU(c, cudaGetLastError());
     if (tracing) cudaEventRecord(tr.r1, c->stream);
     // In a pipeline of launches (tiling) the rest runs on the second stream, next to the render

@@ -42,14 +42,6 @@ constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 // because every phase that pushes to them starts only while late + orb <= kZJoint (else `late`
 // runs first, with whatever it holds).
 constexpr int kDeepCap = 63;
-// Attracting-cycle certificate (cert_phase): its candidates wait in the deep arrays, growing down
-// from the top; deep + cert <= kDeepArr because `late` pushes to deep only while both fit with 32
-// to spare, and every other push moves entries that were already counted.
-constexpr int kDeepArr = kDeepCap + 16;
-#ifndef BUDDHA_CERT_RUN
-#define BUDDHA_CERT_RUN 24
-#endif
-constexpr int kCertRun = BUDDHA_CERT_RUN;      // the certificate runs on batches of at least this many
 constexpr int kZCap = 87, kZJoint = kZCap - 32;
 constexpr int kCCap = 94;
 constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel with < 32 accepted samples
@@ -132,6 +124,12 @@ struct RenderParams {
   const uint32_t *tile_cap;     // [tile] capacity of each of the tile's lists
   const uint32_t *tile_base;    // [tile] first pool entry of the tile; list w starts at + w * cap
   uint32_t *pool;               // tile-local cell offsets
+  // certificate queues (cert_phase): cert_cap entries per warp of the persistent grid, 0 = off.
+  // Pending samples grow down from the top of a warp's block, failed ones (waiting to return to
+  // `deep`) up from its bottom.  meta = (last, age, period / state, -).
+  double2 *cert_c, *cert_z;
+  uint4 *cert_m;
+  uint32_t cert_cap;
 };
 
 // ---- small helpers --------------------------------------------------------------------------
@@ -463,15 +461,14 @@ render_simple_kernel(RenderParams p, unsigned long long first, uint32_t *__restr
 //   z_*      late (0 up): it = iterations done; orb (kZCap-1 down): it = steps still to record
 //   deep_*   carry their checkpoint, so suspending a lane does not restart the periodicity search
 //            (long cycles need long uninterrupted windows); meta = (last, age): the age after which
-//            no further full round fits below max_it, and the rounds spent in deep so far.
-//            cert (slots kDeepArr-1 down, no deep_r): samples waiting for the cycle certificate
+//            no further full round fits below max_it, and the rounds spent in deep so far
 struct WarpQueues {
-  double2 deep_c[kDeepArr], deep_z[kDeepArr], deep_r[kDeepCap];
+  double2 deep_c[kDeepCap], deep_z[kDeepCap], deep_r[kDeepCap];
   double2 z_c[kZCap], z_z[kZCap];
   union { double2 c_c[kCCap]; uint4 c_w[kCCap]; };
-  uint2 deep_meta[kDeepArr];
+  uint2 deep_meta[kDeepCap];
   int z_it[kZCap];
-  int pad[(4 - (2 * kDeepArr + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
+  int pad[(4 - (2 * kDeepCap + kZCap) % 4) % 4];  // keeps the next warp's arrays 16-byte aligned
   // fused render: this warp's per-channel / per-band accumulators (ChannelSlot), added to the
   // global ones when the kernel ends.  (They used to be global atomics from every late / tier
   // batch: 6 same-address atomics per ~1000 candidates from 10 000 warps.)
@@ -487,7 +484,8 @@ constexpr bool kT0 = false, kT2 = true;     // the two stacks in c_*
 
 // Per-warp state that lives in registers for the whole kernel.
 struct WarpState {
-  int t0_n, t2_n, late_n, deep_n, orb_n, cert_n;  // stack heights (warp-uniform)
+  int t0_n, t2_n, late_n, deep_n, orb_n;  // stack heights (warp-uniform)
+  int pend_n, fail_n;                      // the warp's certificate queue in global memory (see cert_phase)
   unsigned long long chunk_base;           // first sample index of the chunk this warp owns
   uint32_t chunk_off, chunk_len;           // progress inside the chunk
   bool exhausted;                          // the global cursor ran past p.end
@@ -837,7 +835,7 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
     cx = c.x; cy = c.y; x = z.x; y = z.y; it = q.z_it[slot];
   }
   __syncwarp();  // the slots are re-used by the pushes below
-  const bool deep_room = ws.deep_n < 32 && ws.deep_n + ws.cert_n <= kDeepArr - 32;
+  const bool deep_room = ws.deep_n < 32;
   bool alive = act;
   int cnt = 0;
   tested_steps<kVar, kLateSteps>(x, y, cx, cy, alive, cnt);
@@ -876,10 +874,10 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
 // ---- attracting-cycle certificate ---------------------------------------------------------------
 //
 // After the closed-form tests for periods 3 and 4 the never-escaping samples that are left (0.33 %
-// of the candidates on config 2) still cost 10.5 of the 14.1 iterations a candidate executes: they
+// of the candidates on config 2) still cost 10.5 of the 14.4 iterations a candidate executes: they
 // run until their state repeats bit for bit, 3160 iterations on average.  A sample that has spent
-// 4, 16, 64, ... rounds in `deep` is therefore handed to cert_phase, which looks for the attracting
-// cycle itself, lane-parallel on a batch of such samples:
+// 64, 256, 1024, ... rounds in `deep` is therefore parked for cert_phase, which looks for the
+// attracting cycle itself:
 //   1. period: the first k <= pmax with |z_k - z| < kCertTol, iterating in float from the sample's
 //      current state z;
 //   2. Newton on f^p(w) - w in double from w = z, the derivative d = prod 2 w_j carried along the
@@ -890,23 +888,46 @@ __device__ __forceinline__ void late_phase(const RenderParams &p, WarpQueues &q,
 // the orbit of 0 converges to the cycle, and the reference's loop runs to max_iterations whatever
 // that is: `hit max` without iterating further.  Histogram-neutral like the periodicity check and
 // the period-3/4 tests, and evidence of the same kind: the test suite restates it on the CPU
-// (check_certificate) and runs the reference's own loop on every certified sample (0 escapes among 425 000
-// certified in 2 x 2^26 samples; with the multiplier bound at 1.1 the same check finds 195 in 2^22),
-// and every GPU parity test runs with it (and without: BUDDHA_F_NO_SHORTCUT).  Samples the certificate cannot settle
-// (period > pmax, multiplier too close to 1, Newton not converged) go back to `deep` unchanged.
-// On config 2 it settles 96 % of the remaining never-escaping samples, 588 instead of 3160
-// iterations each.
-constexpr unsigned kCertFirstAge = 4;            // tried at ages 4, 16, 64, ... (powers of four)
-constexpr int kCertPmaxFirst = 32, kCertPmaxLater = 64;
+// (check_certificate) and runs the reference's own loop on every certified sample (0 escapes among
+// 161 000 certified in 2 x 2^26 samples from age 64, 0 among 425 000 from age 4; with the
+// multiplier bound at 1.1 the same check finds 44 in 2^22), and every GPU parity test runs with it
+// (and without: BUDDHA_F_NO_SHORTCUT).  Samples the certificate cannot settle (period > pmax,
+// multiplier too close to 1, Newton not converged) go back to `deep` unchanged.
+//
+// When to try.  From age 4 the certificate settles 96 % of these samples (588 instead of 3160
+// iterations each, executed iterations per candidate 14.4 -> 6.1) but config 2 gains only 2 %: a
+// saved deep iteration is worth ~0.18 issue cycles per candidate -- the FP64 chains of `deep` run
+// largely in issue slots the other warps leave free -- while an attempt costs 150-200, and at age
+// 4 four in ten attempts are samples that escape later.  Measured on config 2 at 2^35-sample
+// steps: first age 4 +2.2 %, 16 +4.1 %, 64 +6.5 % (36 % settled, 14.4 -> 9.2 iterations), 256
+// +1.6 %.  At -m 5000 (config 4) and in the 72-register and fused builds it costs 2-10 %, so only
+// render_persistent_kernel<plain, kRegsWide> uses it, for -m >= kCertMinIt.
+#ifndef BUDDHA_CERT_FIRST_AGE
+#define BUDDHA_CERT_FIRST_AGE 64
+#endif
+constexpr unsigned kCertFirstAge = BUDDHA_CERT_FIRST_AGE;  // tried at this age (a power of four) and at 4 x, 16 x, ... it
+#ifndef BUDDHA_CERT_PMAX_FIRST
+#define BUDDHA_CERT_PMAX_FIRST 32
+#endif
+constexpr int kCertPmaxFirst = BUDDHA_CERT_PMAX_FIRST, kCertPmaxLater = 64;
 constexpr int kCertPasses = 5;                   // Newton evaluations (the last one only verifies)
 constexpr float kCertTol = 1e-2f;
 constexpr double kCertResMax = 1e-12, kCertLam2Max = 0.998;
-constexpr int kCertMinIt = 4000;                 // below this -m the bit-exact search is cheaper
+#ifndef BUDDHA_CERT_MIN_IT
+#define BUDDHA_CERT_MIN_IT 8000
+#endif
+constexpr int kCertMinIt = BUDDHA_CERT_MIN_IT;   // below this -m the bit-exact search is cheaper (-m 5000: -3 %)
+constexpr int kCertQueue = 512;                  // queue entries per warp (host side: RenderParams::cert_cap)
+constexpr int kCertHeadroom = 32;                // entries kept free at the top (cert_phase, stage C)
+#ifndef BUDDHA_CERT_GANG
+#define BUDDHA_CERT_GANG 12
+#endif
+constexpr int kCertGang = BUDDHA_CERT_GANG;      // lanes that wait at the end of a Newton pass before it is handled
 
 // the next age at which a sample of age `age` is due for the certificate: the smallest power of
 // four >= kCertFirstAge that is > age
 __device__ __forceinline__ unsigned next_cert_age(unsigned age) {
-  return 1u << (((31 - __clz((int)(age | 1u))) & ~1) + 2);
+  return max(kCertFirstAge, 1u << (((31 - __clz((int)(age | 1u))) & ~1) + 2));
 }
 
 // Checkpoint schedule of the periodicity search: a new checkpoint after 1, 2, 3, 4, 6, 8, 12, 16,
@@ -933,12 +954,15 @@ __device__ __forceinline__ bool checkpoint_age(unsigned age) {
 // stale orbit may run to inf/NaN, which costs nothing on this hardware).
 template <int kVar, bool kCert>
 __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                           bool drain, unsigned long long *counters) {
+                                           bool drain, bool park, unsigned long long *counters,
+                                           uint32_t gwarp) {
   static_assert(kLateSteps == kBlock, "late batches and deep rounds must have the same length");
   const int max_it = p.max_it;
   const int m24 = max_it - (max_it - kT2End) % kBlock;
   const bool shortcut = p.shortcut != 0;
-  const bool cert_on = kCert && shortcut && max_it >= kCertMinIt;
+  // (park = false once the sample range is used up: a sample parked then would only come back
+  //  after everything else has drained, and the tail of a launch is as long as its longest chain)
+  const bool cert_on = kCert && park && shortcut && p.cert_cap != 0u;
   bool act = false;
   double cx = 0.0, cy = 0.0, x = 0.0, y = 0.0, rx = 0.0, ry = 0.0;
   unsigned age = 0;     // rounds this sample has spent in deep (checkpoint schedule)
@@ -1003,16 +1027,21 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
         push_z<kLate>(q, ws.late_n, back, cx, cy, out ? x0 : x, out ? y0 : y, out ? it - kBlock : it);
       act = act && !fin;
       if constexpr (kCert) {
-        // due for the cycle certificate: suspended onto the cert stack (top of the deep arrays)
-        const bool due = act && cert_on && age_now == ev;
-        const unsigned dm = __ballot_sync(kFull, due);
+        // due for the cycle certificate: suspended into the warp's queue in global memory (as many
+        // as fit; the others carry on and are due again at the next certificate age)
+        const bool due0 = act && cert_on && age_now == ev;
+        const unsigned dm = __ballot_sync(kFull, due0);
         if (dm) {
-          const int slot = kDeepArr - 1 - (ws.cert_n + __popc(dm & lanemask_lt()));
-          ws.cert_n += __popc(dm);
+          const int room = (int)p.cert_cap - kCertHeadroom - ws.pend_n - ws.fail_n;
+          const int rank = __popc(dm & lanemask_lt());
+          const bool due = due0 && rank < room;
           if (due) {
-            q.deep_c[slot] = make_double2(cx, cy); q.deep_z[slot] = make_double2(x, y);
-            q.deep_meta[slot] = make_uint2(last, age_now);
+            const size_t idx = (size_t)gwarp * p.cert_cap + (p.cert_cap - 1u - (uint32_t)(ws.pend_n + rank));
+            __stcg(p.cert_c + idx, make_double2(cx, cy)); __stcg(p.cert_z + idx, make_double2(x, y));
+            __stcg(p.cert_m + idx, make_uint4(last, age_now, 0u, 0u));
           }
+          if (due0 && !due) ev = min(last, next_cert_age(age_now));
+          ws.pend_n += max(min(__popc(dm), room), 0);
           ws.d_rounds += due ? (int32_t)age_now : 0;
           act = act && !due;
         }
@@ -1026,32 +1055,57 @@ __device__ __forceinline__ void deep_phase(const RenderParams &p, WarpQueues &q,
   __syncwarp();
 }
 
-// (c') the cycle certificate on a batch of up to 32 suspended deep samples (see above).  Certified
-// samples are `hit max`; the others return to `deep` with their state, age and schedule (the
-// checkpoint restarts at the current state: every certificate age is a checkpoint age anyway).
+// (c') the cycle certificate over the warp's queue of suspended deep samples (see above).
+//
+// The work per sample is (Newton passes) x (period) derivative steps, anything from 2 to 320, so a
+// batch of 32 in lockstep runs at the pace of its slowest member (measured: 5 passes x ~54 steps
+// for every batch, more than the iterations saved on all but config 2).  The samples are therefore
+// collected in a queue of p.cert_cap entries per warp in global memory (they are rare: 0.17 % of
+// the candidates from age 64, 48 bytes each) and worked off a few hundred at a time:
+//   A. period search, 32 entries in lockstep, the period written back into the entry;
+//   B. Newton with PER-LANE REFILL: a lane that has settled its sample takes the next entry that
+//      has a period, so the cost follows the mean work, not the maximum;
+//   C. the entries that got no certificate are compacted to the bottom of the queue, from where
+//      reinject_phase returns them to `deep` (32 at a time, whenever deep has room) with their
+//      state, age and schedule; the checkpoint restarts at the current state (every certificate
+//      age is a checkpoint age anyway).
+// Certified samples are `hit max`.
+constexpr uint32_t kCertDone = 0xffffffffu;      // meta.z: 0 = no certificate, 1..64 = period found
+constexpr double kCertHopeless = 1e-6;           // residual^2 (scaled) a lane must have reached after 2 passes
+
+// position of the n-th (0-based) set bit of m, which has more than n bits set
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
+  int pos = 0;   // the largest t with at most n set bits below bit t
+#pragma unroll
+  for (int b = 16; b >= 1; b >>= 1)
+    if (__popc(m & ((1u << (pos + b)) - 1u)) <= n) pos += b;
+  return pos;
+}
+
+// The queues are read and written through L2 (ld.cg / st.cg): an entry is written by one lane and
+// read by another lane of the same warp, phases apart.
 template <int kVar>
-__device__ __forceinline__ void cert_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
-                                           unsigned long long *counters) {
-  const int take = min(ws.cert_n, 32);
-  const bool act = (int)lane_id() < take;
-  ws.cert_n -= take;
-  double cx = 0.0, cy = 0.0, zx = 0.0, zy = 0.0;
-  unsigned last = 0, age = 0;
-  if (act) {
-    const int slot = kDeepArr - 1 - (ws.cert_n + (int)lane_id());
-    const double2 c = q.deep_c[slot], z = q.deep_z[slot];
-    const uint2 meta = q.deep_meta[slot];
-    cx = c.x; cy = c.y; zx = z.x; zy = z.y; last = meta.x; age = meta.y;
-  }
+__device__ __forceinline__ void cert_phase(const RenderParams &p, WarpState &ws,
+                                           unsigned long long *counters, uint32_t gwarp) {
+  const int n = ws.pend_n;                       // entries [cap - n, cap) of the warp's block
+  const size_t base = (size_t)gwarp * p.cert_cap + (p.cert_cap - (uint32_t)n);
+  const int lane = (int)lane_id();
   __syncwarp();
-  const double x_in = zx, y_in = zy;
-  // 1. period search in float
-  const int pmax = act ? (age == kCertFirstAge ? kCertPmaxFirst : kCertPmaxLater) : 0;
-  int per = 0;
-  {
-    const float fcx = (float)cx, fcy = (float)cy, fx0 = (float)zx, fy0 = (float)zy;
+  // A. period search in float: the first k <= pmax with |z_k - z| < kCertTol
+#pragma unroll 1
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const bool act = c0 + lane < n;
+    double2 c = make_double2(0.0, 0.0), z = make_double2(0.0, 0.0);
+    unsigned age = 0;
+    if (act) {
+      c = __ldcg(p.cert_c + base + c0 + lane); z = __ldcg(p.cert_z + base + c0 + lane);
+      age = __ldcg(&p.cert_m[base + c0 + lane].y);
+    }
+    const int pmax = act ? (age == kCertFirstAge ? kCertPmaxFirst : kCertPmaxLater) : 0;
+    const float fcx = (float)c.x, fcy = (float)c.y, fx0 = (float)z.x, fy0 = (float)z.y;
     const float tol2 = 4.0f * kCertTol * kCertTol;   // scaled state: distances are doubled
     float fx = fx0, fy = fy0;
+    int per = 0;
 #pragma unroll 1
     for (int k0 = 0; k0 < kCertPmaxLater; k0 += 8) {
 #pragma unroll
@@ -1064,48 +1118,131 @@ __device__ __forceinline__ void cert_phase(const RenderParams &p, WarpQueues &q,
       if (__all_sync(kFull, per != 0 || k0 + 8 >= pmax)) break;
     }
     if (per > pmax) per = 0;
+    if (act) __stcg(&p.cert_m[base + c0 + lane].z, (uint32_t)per);
   }
-  // 2. Newton on f^per(w) - w, all lanes in lockstep over the longest period of the batch
-  const int maxp = __reduce_max_sync(kFull, per);
-  double rx = 1.0, ry = 1.0, dr = 1.0, di = 0.0;   // residual (scaled) and multiplier at the last iterate
-  const double res2_max = kCertResMax * kCertResMax;
-  if (maxp > 0) {
+  __syncwarp();
+  // B. Newton on f^per(w) - w in double, the derivative d = prod 2 w_j carried along
+  {
+    const double res2_max = kCertResMax * kCertResMax;
+    const int max_it = p.max_it;
+    const int m24 = max_it - (max_it - kT2End) % kBlock;
+    bool act = false;
+    double cx = 0.0, cy = 0.0, zx = 0.0, zy = 0.0, x = 0.0, y = 0.0, dr = 1.0, di = 0.0;
+    int per = 0, k = 0, pass = 0, mine = 0, it_done = 0;
+    int cursor = 0, chunk0 = 0;
+    unsigned avail = 0u;                         // entries of chunk0 .. chunk0+31 with a period, not yet taken
 #pragma unroll 1
-    for (int pass = 0; pass < kCertPasses; pass++) {
-      double x = zx, y = zy;
-      dr = 1.0; di = 0.0;
+    for (;;) {
+      unsigned idle = __ballot_sync(kFull, !act);
 #pragma unroll 1
-      for (int k = 0; k < maxp; k++) {
-        if (k < per) {
+      while (idle != 0u) {
+        if (avail == 0u) {
+          if (cursor >= n) break;
+          const uint32_t pe = (cursor + lane < n) ? __ldcg(&p.cert_m[base + cursor + lane].z) : 0u;
+          avail = __ballot_sync(kFull, pe != 0u);
+          chunk0 = cursor; cursor += 32;
+          continue;
+        }
+        const int rank = __popc(idle & lanemask_lt()), na = __popc(avail);
+        if (!act && rank < na) {
+          mine = chunk0 + nth_set_bit(avail, rank);
+          const double2 c = __ldcg(p.cert_c + base + mine), z = __ldcg(p.cert_z + base + mine);
+          const uint4 m = __ldcg(p.cert_m + base + mine);               // (last, age, period, -)
+          per = (int)m.z;
+          it_done = m24 - (int)(m.x - m.y) * kBlock;                    // iterations the sample has done
+          cx = c.x; cy = c.y; zx = z.x; zy = z.y; x = zx; y = zy; dr = 1.0; di = 0.0;
+          k = 0; pass = 0; act = true;
+        }
+        // the lowest popc(idle) entries of `avail` are taken now
+        avail = __ballot_sync(kFull, ((avail >> lane) & 1u) != 0u &&
+                                         __popc(avail & lanemask_lt()) >= __popc(idle));
+        idle = __ballot_sync(kFull, !act);
+      }
+      const unsigned am = __ballot_sync(kFull, act);
+      if (am == 0u) break;
+      // derivative steps.  A lane that has completed its period waits; the pass-end handling below
+      // (~80 issue cycles, ~230 when lanes finish and refill, against 23 per step) runs once
+      // kCertGang lanes are waiting, or all of them.
+      unsigned waiting;
+#pragma unroll 1
+      do {
+        if (act && k < per) {
           const double ndr = __fma_rn(x, dr, -__dmul_rn(y, di)), ndi = __fma_rn(x, di, __dmul_rn(y, dr));
           dr = ndr; di = ndi;
           zstep<false>(x, y, cx, cy);
+          k++;
         }
+        waiting = __ballot_sync(kFull, act && k == per);
+      } while (__popc(waiting) < kCertGang && waiting != am);
+      // end of a pass: accept, give up, or take the Newton step
+      const bool e = act && k == per;
+      const double rx = __dsub_rn(x, zx), ry = __dsub_rn(y, zy);           // residual (scaled)
+      const double res2 = __fma_rn(ry, ry, __dmul_rn(rx, rx));
+      const bool conv = res2 < res2_max;
+      const bool ok = e && conv && __fma_rn(di, di, __dmul_rn(dr, dr)) < kCertLam2Max;
+      const bool giveup = e && !ok && (conv || pass + 1 >= kCertPasses ||
+                                       (pass >= 1 && !(res2 < kCertHopeless)));  // (true for NaN)
+      if (e && !ok && !giveup) {
+        const double er = __dsub_rn(dr, 1.0), ei = di;
+        // (an approximate reciprocal is enough: a slightly inexact Newton step still contracts)
+        const double inv = (double)__frcp_rn((float)__fma_rn(er, er, __dmul_rn(ei, ei)));
+        // w <- w - r / (d - 1) = w - r conj(d - 1) / |d - 1|^2
+        zx = __dsub_rn(zx, __dmul_rn(__fma_rn(rx, er, __dmul_rn(ry, ei)), inv));
+        zy = __dsub_rn(zy, __dmul_rn(__fma_rn(ry, er, -__dmul_rn(rx, ei)), inv));
+        x = zx; y = zy; dr = 1.0; di = 0.0; k = 0; pass++;
       }
-      rx = __dsub_rn(x, zx); ry = __dsub_rn(y, zy);
-      const bool conv = __fma_rn(ry, ry, __dmul_rn(rx, rx)) < res2_max;
-      if (pass + 1 == kCertPasses || __all_sync(kFull, per == 0 || conv)) break;
-      const double er = __dsub_rn(dr, 1.0), ei = di;
-      // (an approximate reciprocal is enough: a slightly inexact Newton step still contracts)
-      const double inv = (double)__frcp_rn((float)__fma_rn(er, er, __dmul_rn(ei, ei)));
-      // w <- w - r / (d - 1) = w - r conj(d - 1) / |d - 1|^2
-      zx = __dsub_rn(zx, __dmul_rn(__fma_rn(rx, er, __dmul_rn(ry, ei)), inv));
-      zy = __dsub_rn(zy, __dmul_rn(__fma_rn(ry, er, -__dmul_rn(rx, ei)), inv));
+      if (__ballot_sync(kFull, ok || giveup)) {
+        if (ok) {
+          ws.n_hit += 1u; ws.n_cyc += 1u;
+          ws.skipped += (uint32_t)(max_it - it_done);
+          __stcg(&p.cert_m[base + mine].z, kCertDone);
+        } else if (giveup) {
+          __stcg(&p.cert_m[base + mine].z, 0u);
+        }
+        act = act && !(ok || giveup);
+        if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);  // (huge -m)
+      }
     }
   }
-  // 3. certified: an attracting cycle (NaN compares false)
-  const bool ok = act && per > 0 && __fma_rn(ry, ry, __dmul_rn(rx, rx)) < res2_max &&
-                  __fma_rn(di, di, __dmul_rn(dr, dr)) < kCertLam2Max;
-  {
-    const int max_it = p.max_it;
-    const int m24 = max_it - (max_it - kT2End) % kBlock;
-    const int it = m24 - (int)(last - age) * kBlock;   // iterations the sample has done
-    ws.n_hit += ok ? 1u : 0u;
-    ws.n_cyc += ok ? 1u : 0u;
-    ws.skipped += ok ? (uint32_t)(max_it - it) : 0u;
+  __syncwarp();
+  // C. the entries without a certificate move to the bottom of the block.  Chunks are read from
+  // the lowest pending index upwards, so the write position (at most the number of entries read
+  // before this chunk) stays below everything unread; kCertHeadroom keeps it below the chunk
+  // being read as well.
+  int f = 0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const bool act = c0 + lane < n;
+    uint4 m = make_uint4(0u, 0u, kCertDone, 0u);
+    double2 c = make_double2(0.0, 0.0), z = make_double2(0.0, 0.0);
+    if (act) m = __ldcg(p.cert_m + base + c0 + lane);
+    const bool failed = act && m.z == 0u;
+    if (failed) { c = __ldcg(p.cert_c + base + c0 + lane); z = __ldcg(p.cert_z + base + c0 + lane); }
+    const unsigned fm = __ballot_sync(kFull, failed);   // (also orders the loads before the stores)
+    if (failed) {
+      const size_t dst = (size_t)gwarp * p.cert_cap + (size_t)(f + __popc(fm & lanemask_lt()));
+      __stcg(p.cert_c + dst, c); __stcg(p.cert_z + dst, z); __stcg(p.cert_m + dst, m);
+    }
+    f += __popc(fm);
   }
-  push_deep(q, ws, act && !ok, cx, cy, x_in, y_in, x_in, y_in, last, age);
-  if (__ballot_sync(kFull, (ws.skipped >> 30) != 0u)) flush_counters(ws, counters);  // (huge -m)
+  ws.fail_n = f;
+  ws.pend_n = 0;
+  __syncwarp();
+}
+
+// Returns up to 32 samples that got no certificate to `deep` (which holds < 32 entries here).
+__device__ __forceinline__ void reinject_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
+                                               uint32_t gwarp) {
+  const int take = min(ws.fail_n, 32);
+  const bool act = (int)lane_id() < take;
+  double2 c = make_double2(0.0, 0.0), z = make_double2(0.0, 0.0);
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);
+  if (act) {
+    const size_t idx = (size_t)gwarp * p.cert_cap + (size_t)(ws.fail_n - 1 - (int)lane_id());
+    c = __ldcg(p.cert_c + idx); z = __ldcg(p.cert_z + idx); m = __ldcg(p.cert_m + idx);
+  }
+  ws.fail_n -= take;
+  push_deep(q, ws, act, c.x, c.y, z.x, z.y, z.x, z.y, m.x, m.y);
   __syncwarp();
 }
 
@@ -1240,7 +1377,7 @@ constexpr size_t kQueueBytes = sizeof(WarpQueues) * kWarpsPerCta;
 // side kernels of launch k could only start when launch k+1 had finished (measured: 20000x20000
 // -m 20000 3.7e10 -> 4.4e10 samples/s, -m 2000 5.5e10 -> 7.6e10).
 constexpr int kRegsWide = 80, kRegsLean = 72;
-template <int kVar, int kMaxReg>
+template <int kVar, int kMaxReg, bool kCertBuild = false>
 __global__ void __maxnreg__(kMaxReg)
 render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
                          unsigned long long *__restrict__ cursor,
@@ -1257,7 +1394,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
     __syncwarp();
   }
   WarpState ws;
-  ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = ws.cert_n = 0;
+  ws.t0_n = ws.t2_n = ws.late_n = ws.deep_n = ws.orb_n = ws.pend_n = ws.fail_n = 0;
   if (spill.carry_in) {  // the orbits this warp parked at the end of the previous launch
     // (the broadcast tells the compiler the count is warp-uniform: without it every vote in the
     //  scheduler loop below is compiled with a divergence fallback, +40 % code, -5 % speed)
@@ -1281,8 +1418,10 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
 #pragma unroll
   for (int k = 0; k < kMaxBands; k++) ws.ch_inc[k] = 0;
 
-  // (the certificate, like the period-4 test, only pays in the plain 80-register build so far)
-  constexpr bool kCertBuild = kVar == 0 && kMaxReg == kRegsWide;
+  // kCertBuild: the build with the cycle certificate (cert_phase).  Like the period-4 test it only
+  // pays in the plain 80-register build, and only for large -m, so it is a separate instantiation:
+  // contexts that do not use it run the kernel without its code (config 1 and 4 measured 4 % slower
+  // with the certificate's code merely present).
 #pragma unroll 1
   for (;;) {
     // strict priority along the push graph: a phase is reached only when every stack it pushes
@@ -1294,14 +1433,16 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
       orbit_phase<kVar>(p, q, ws, sink);
     } else if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint || (dry2 && ws.late_n > 0)) {
       late_phase<kVar, (kMaxReg == kRegsWide) && (kVar & kVarFused) == 0>(p, q, ws, counters);
-    } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0)) {
-      deep_phase<kVar, kCertBuild>(p, q, ws, dry3, counters);
-    } else if (kCertBuild &&
-               (ws.cert_n >= kCertRun ||
-                (ws.cert_n > 0 && (dry3 || ws.deep_n + ws.cert_n > kDeepArr - 32)))) {
-      // (the last condition: `late` may not push to deep while the shared arrays are this full,
-      //  and deep itself holds < 32 here, so the waiting certificates have to make room)
-      cert_phase<kVar>(p, q, ws, counters);
+    } else if (ws.deep_n >= 32 || (dry3 && ws.deep_n > 0 && ws.fail_n == 0 && ws.pend_n == 0)) {
+      // (at the end the parked samples are settled first -- one certificate pass over the queue,
+      //  the rest back into deep -- so that everything left drains together)
+      deep_phase<kVar, kCertBuild>(p, q, ws, dry3 && ws.fail_n == 0 && ws.pend_n == 0, !dry3,
+                                   counters, sink.gwarp);
+    } else if (kCertBuild && ws.fail_n > 0) {
+      reinject_phase(p, q, ws, sink.gwarp);     // (deep holds < 32 here)
+    } else if (kCertBuild && ws.pend_n > 0 &&
+               (dry3 || ws.pend_n >= (int)p.cert_cap - kCertHeadroom - 64)) {
+      cert_phase<kVar>(p, ws, counters, sink.gwarp);   // (no failed entries left here)
     } else if (ws.t2_n >= 32 || (dry1 && ws.t2_n > 0)) {
       tier_phase<kVar, kT1End, kT2End - kT1End, true>(p, q, ws, ws.t2_n, counters);
     } else if (ws.t0_n >= 32 || (dry && ws.t0_n > 0)) {

@@ -214,7 +214,7 @@ def check_period4(seed, first, count, max_iter, mu_max=0.999 / 16):
 
 
 def check_certificate(seed, first, count, max_iter, lam2_max=0.998, pmax=(32, 64), tol=1e-2, passes=5,
-                      res_max=1e-12, first_age=4, age_factor=4):
+                      res_max=1e-12, first_age=64, age_factor=4):
     """(certified samples that escaped -- must be 0, stats): the evidence behind the kernel's
     attracting-cycle certificate (buddha_kernels.cuh: cert_phase), tried where the kernel tries it.
     stats: not_rejected, inset (never-escaping, not flagged by the period-3/4 tests), certified,

@@ -237,11 +237,18 @@ def test_cycle_certificate_is_conservative(oracle):
     (period search in float, Newton in double, residual < 1e-12, |multiplier|^2 < 0.998): c then lies
     in a hyperbolic component.  Every certified sample must run the reference's loop
     (cudabrot.cu:319-340) to max_iterations; a multiplier bound beyond 1 must be caught by this very
-    check.  The certificate has to settle most of what the closed-form period-3/4 tests leave."""
+    check.  Tried where the kernel tries it (from deep age 64) and from age 4, where it has to
+    settle nearly everything the closed-form period-3/4 tests leave."""
     for seed, first in ((1337, 0), (99, 1 << 40)):
         bad, st = oracle.check_certificate(seed, first, 1 << 22, 20000)
+        assert bad == 0
+        assert st["certified"] > 0.3 * st["inset"]          # the rest turns bit-periodic before age 64
+        assert st["iters_cert"] < 0.6 * st["iters_exact"]
+        bad, st = oracle.check_certificate(seed, first, 1 << 22, 20000, first_age=4)
         assert bad == 0
         assert st["certified"] > 0.93 * st["inset"]
         assert st["iters_cert"] < 0.25 * st["iters_exact"]
     bad, _ = oracle.check_certificate(1337, 0, 1 << 22, 20000, lam2_max=1.1)
+    assert bad > 0
+    bad, _ = oracle.check_certificate(1337, 0, 1 << 22, 20000, lam2_max=1.1, first_age=4)
     assert bad > 0

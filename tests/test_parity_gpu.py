@@ -223,11 +223,12 @@ def test_full_size_cfg3_histogram(buddha, oracle):
     assert int(hist.sum(dtype=np.uint64)) == cnt["increments"]
 
 
-def test_full_size_properties_cfg2(buddha):
+def test_full_size_properties_cfg2(buddha, monkeypatch):
     """BASELINE config 2 at its full canvas and 2^30 samples, where the oracle would need minutes:
     size-independent properties instead.  One call == any split into calls; the histogram sum ==
     the increments counted; every candidate ends in exactly one class; the exact shortcut and the
-    division-free binning change nothing (checked on a 2^27-sample prefix)."""
+    division-free binning change nothing (checked on a 2^27-sample prefix), nor does the size of the
+    certificate queues."""
     w = h = 4000
     n = 1 << 30
     with buddha.Renderer(w, h, 20000, 10000) as r:
@@ -258,6 +259,17 @@ def test_full_size_properties_cfg2(buddha):
             assert np.array_equal(ref[0], hist)
             for k in COUNTER_KEYS:
                 assert ref[1][k] == c[k], k
+    # the cycle certificate with its smallest queue (160 entries per warp): at this sample count
+    # the queues fill and are worked off several times per warp (with the default 512 only the
+    # single 2^30-sample call above gets there)
+    monkeypatch.setenv("BUDDHA_CERT_QUEUE", "160")
+    with buddha.Renderer(w, h, 20000, 10000) as r:
+        r.render_samples(1 << 40, m)
+        hist, c = r.read_histogram(), r.counters()
+    assert np.array_equal(ref[0], hist)
+    for k in COUNTER_KEYS:
+        assert ref[1][k] == c[k], k
+    assert c["executed_iters"] < ref[1]["executed_iters"]      # (ref[1]: the run with every shortcut)
 
 
 def test_full_size_properties_cfg3_tiled_vs_direct(buddha, monkeypatch):
