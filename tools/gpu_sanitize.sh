@@ -3,7 +3,7 @@
 # hazards in the warp-synchronous stacks), synccheck.  Plain, tiled, fused and ship variants.
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
-import sys, numpy as np
+import os, sys, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import cudabrot_b200 as B
 def run(**kw):
@@ -19,6 +19,10 @@ run(width=200, height=150, channels=[(100, 20), (1000, 20), (3000, 50)])
 run(width=200, height=150, channels=[(100, 20), (1000, 20)], flags=B.F_FORCE_TILED | B.F_BURNING_SHIP)
 run(width=64, height=64, max_iterations=5, min_iterations=0, n=5000)
 run(width=64, height=48, max_iterations=400, min_iterations=20, n=1 << 16)   # privatised copies
+# round 2: the cycle certificate (queues in global memory, per-lane refill, re-injection into deep)
+os.environ["BUDDHA_CERT_QUEUE"] = "160"
+run(width=200, height=150, max_iterations=9000, min_iterations=20, n=1 << 18)
+del os.environ["BUDDHA_CERT_QUEUE"]
 # round 2: a pipeline of tiled launches with orbit carry-over (1 MB list pool -> many launches)
 import os
 os.environ["BUDDHA_TILE_POOL_MB"] = "1"
