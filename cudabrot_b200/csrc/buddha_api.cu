@@ -37,7 +37,7 @@ constexpr uint32_t kLutMax = 1u << 18;  // counts below this are tone-mapped thr
 constexpr int kTotalCnt = kCntSlots + kMaxBands * kChSlots;  // common + per-channel / per-band accumulators
 
 struct FastBin {
-  double inv_half, c0_lo, c0_hi;
+  double inv_half, c0;
   bool ok;
 };
 
@@ -129,14 +129,14 @@ int fail(buddha_ctx *ctx, int code, const char *fmt, ...) {
 FastBin make_fast_bin(double min_v, double delta, int n) {
   FastBin f;
   f.ok = false;
-  f.inv_half = f.c0_lo = f.c0_hi = 0.0;
+  f.inv_half = 0.0;
+  f.c0 = nan("");                                    // (no point is "in range": every one takes bin_exact)
   double inv = 1.0 / delta;
   if (!(inv > 0.0) || !isfinite(inv)) return f;
   if (n > (1 << 19)) return f;                       // quotient must stay below 2^20
   if (!(fabs(min_v) * inv < 0x1p36)) return f;       // keeps |c0| in the 2^40 binade, errors < 2^-12
   long double base = (long double)0x1.8p40 - (long double)min_v * (long double)inv;
-  f.c0_hi = (double)(base + (long double)0x1p-11);
-  f.c0_lo = (double)(base - (long double)0x1p-11);
+  f.c0 = (double)(base + (long double)0x1p-11);     // the upper side: T - 2^-10 < Q < T
   f.inv_half = inv * 0.5;
   f.ok = true;
   return f;
@@ -152,8 +152,9 @@ void fill_render_params(buddha_ctx *c) {
   FastBin fr = make_fast_bin(p.min_real, c->delta_re, p.width);
   FastBin fi = make_fast_bin(p.min_imag, c->delta_im, p.height);
   r.fast_bin = (fr.ok && fi.ok && !(p.flags & BUDDHA_F_EXACT_BINNING)) ? 1 : 0;
-  r.inv_half_re = fr.inv_half; r.c0_lo_re = fr.c0_lo; r.c0_hi_re = fr.c0_hi;
-  r.inv_half_im = fi.inv_half; r.c0_lo_im = fi.c0_lo; r.c0_hi_im = fi.c0_hi;
+  r.inv_half_re = fr.inv_half; r.c0_re = fr.c0;
+  r.inv_half_im = fi.inv_half; r.c0_im = fi.c0;
+  if (!r.fast_bin) r.c0_re = r.c0_im = nan("");
   r.max_it = p.max_iterations; r.min_it = p.min_iterations;
   r.shortcut = (p.flags & BUDDHA_F_NO_SHORTCUT) ? 0 : 1;
   r.ship = (p.flags & BUDDHA_F_BURNING_SHIP) ? 1 : 0;

@@ -69,6 +69,7 @@ constexpr int kOrbStepBits = 28;               // fused: orbit entries carry (ba
 // Fast binning: T = fma(X, inv_half, C0) lands in [1.5*2^40, 1.5*2^40 + 2^20) for in-range
 // quotients, where the low mantissa word holds quotient * 2^12.
 constexpr int kBinFracBits = 12;
+constexpr uint32_t kBinClearMask = 0xffcu;     // fraction bits that must not all be zero (>= 2^-10)
 constexpr uint32_t kBinHiWord = 0x42780000u;   // high word of 1.5 * 2^40
 
 enum CounterSlot {
@@ -86,7 +87,7 @@ struct RenderParams {
   double min_re, min_im, delta_re, delta_im;
   // fast binning constants (host-computed, see buddha_api.cu: make_fast_bin)
   double inv_half_re, inv_half_im;
-  double c0_lo_re, c0_hi_re, c0_lo_im, c0_hi_im;
+  double c0_re, c0_im;          // (NaN when the canvas does not admit the fast path: nothing is "in range")
   int32_t fast_bin;
   int32_t max_it, min_it;
   int32_t shortcut;
@@ -136,6 +137,12 @@ struct RenderParams {
 
 __device__ __forceinline__ void red_add_u32(uint32_t *addr) {
   asm volatile("red.global.add.u32 [%0], 1;" ::"l"(addr) : "memory");
+}
+
+// The same, predicated inside the instruction stream: no branch around it.
+__device__ __forceinline__ void red_add_u32_if(uint32_t *addr, bool pred) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.global.add.u32 [%0], 1; }"
+               ::"l"(addr), "r"((unsigned)pred) : "memory");
 }
 
 __device__ __forceinline__ unsigned lane_id() {
@@ -300,8 +307,10 @@ struct Sink {
   uint32_t gwarp;      // global warp index = list column
 };
 
+// kDirect: the build of contexts that never tile (the 80-register one): the reduction only.
+template <bool kDirect = false>
 __device__ __forceinline__ void scatter(const RenderParams &p, const Sink &k, uint32_t idx) {
-  if (p.tile_shift) {
+  if (!kDirect && p.tile_shift) {
     uint2 *e = k.tile_tab + (idx >> p.tile_shift);
     const uint32_t slot = atomicAdd(&e->x, 1u);
     if (slot < e->y) {
@@ -358,11 +367,12 @@ __device__ __forceinline__ bool bin_exact_index(double x2, double y2, const Rend
   return false;
 }
 
+template <bool kDirect = false>
 __device__ __forceinline__ bool bin_exact(double x2, double y2, const RenderParams &p,
                                           const Sink &hist) {
   uint32_t idx;
   if (!bin_exact_index(x2, y2, p, &idx)) return false;
-  scatter(p, hist, idx);
+  scatter<kDirect>(p, hist, idx);
   return true;
 }
 
@@ -1258,32 +1268,29 @@ struct OrbitLane {
   uint32_t inc;  // fused render: in-canvas points of this orbit not yet credited to its channels
 };
 
-// Division-free binning of one orbit point.  For each axis two roundings of (quotient +- 2^-11)
-// onto a 2^-12 grid are produced by one DFMA each; if both floors agree, that floor is the
-// reference's truncated IEEE quotient, otherwise the point takes
-// bin_exact_index.  The common path is branch-free (the increment is a predicated reduction), so
-// the binning of one point is scheduled into the latency shadow of the next step's FP64 chain; only
-// the rare exact-binning case branches.
+// Division-free binning of one orbit point.  Per axis ONE DFMA gives T = rn(quotient + 2^-11) on a
+// 2^-12 grid, on the upper side of the reference's IEEE quotient Q: T - 2^-10 < Q < T (DESIGN.md
+// section 4).  If T has left the binade the point is certainly outside; if its fraction is at least
+// 2^-10 (any of the bits in kBinClearMask set) then floor(T) = trunc(Q); in the remaining sliver
+// (2^-10 of a pixel per axis, exact pixel boundaries included) the point takes bin_exact_index,
+// the reference arithmetic verbatim.  (Round 1 formed both T+ and T- = rn(quotient - 2^-11) and
+// compared their floors: the same sliver for two more DFMAs and six more integer instructions.)
+// The common path is branch-free in the build that never tiles (kDirect: a predicated reduction).
 // (fused render: o.n carries the band above bit kOrbStepBits; the point goes to that band's
 // histogram)
-template <int kVar>
+template <int kVar, bool kDirect>
 __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                           const Sink &hist) {
-  const double tch = __fma_rn(o.x, p.inv_half_re, p.c0_hi_re);
-  const double tcl = __fma_rn(o.x, p.inv_half_re, p.c0_lo_re);
-  const double trh = __fma_rn(o.y, p.inv_half_im, p.c0_hi_im);
-  const double trl = __fma_rn(o.y, p.inv_half_im, p.c0_lo_im);
-  const uint32_t ch = (uint32_t)__double2loint(tch), cl = (uint32_t)__double2loint(tcl);
-  const uint32_t rh = (uint32_t)__double2loint(trh), rl = (uint32_t)__double2loint(trl);
-  const bool inrange = ((uint32_t)__double2hiint(tch) == kBinHiWord) &
-                       ((uint32_t)__double2hiint(trh) == kBinHiWord);
-  const bool same = ((((ch ^ cl) | (rh ^ rl)) >> kBinFracBits) == 0u) &
-                    ((uint32_t)__double2hiint(tcl) == kBinHiWord) &
-                    ((uint32_t)__double2hiint(trl) == kBinHiWord);
+  const double tc = __fma_rn(o.x, p.inv_half_re, p.c0_re);
+  const double tr = __fma_rn(o.y, p.inv_half_im, p.c0_im);
+  const uint32_t ch = (uint32_t)__double2loint(tc), rh = (uint32_t)__double2loint(tr);
+  const bool inrange = ((uint32_t)__double2hiint(tc) == kBinHiWord) &
+                       ((uint32_t)__double2hiint(tr) == kBinHiWord);   // (false for the NaN constants)
+  const bool clear = ((ch & kBinClearMask) != 0u) & ((rh & kBinClearMask) != 0u);
   const uint32_t col = ch >> kBinFracBits, row = rh >> kBinFracBits;
-  const bool fast = o.act && p.fast_bin != 0;
-  const bool hit = fast && inrange && same && col < (uint32_t)p.w && row < (uint32_t)p.h;
-  const bool slow = o.act && (p.fast_bin == 0 || (inrange && !same));
+  // (bitwise on purpose: no short-circuit branches in the common path)
+  const bool hit = o.act & inrange & clear & (col < (uint32_t)p.w) & (row < (uint32_t)p.h);
+  const bool slow = o.act & ((p.fast_bin == 0) | (inrange & !clear));
   if constexpr ((kVar & kVarFused) != 0) {
     uint32_t idx = row * (uint32_t)p.w + col;
     bool in = hit;
@@ -1292,13 +1299,17 @@ __device__ __forceinline__ void orbit_bin(const RenderParams &p, OrbitLane &o, W
       in = bin_exact_index(o.x, o.y, p, &idx);
     }
     o.inc += in ? 1u : 0u;
-    if (in) scatter(p, hist, idx + ((unsigned)o.n >> kOrbStepBits) * p.band_stride);
+    if (in) scatter<kDirect>(p, hist, idx + ((unsigned)o.n >> kOrbStepBits) * p.band_stride);
   } else {
-    if (hit) scatter(p, hist, row * (uint32_t)p.w + col);
+    if constexpr (kDirect) {
+      red_add_u32_if(hist.hist + (row * (uint32_t)p.w + col), hit);
+    } else {
+      if (hit) scatter<false>(p, hist, row * (uint32_t)p.w + col);
+    }
     ws.p_inc += hit ? 1u : 0u;
     if (slow) {
       ws.n_exact += 1u;
-      ws.p_inc += bin_exact(o.x, o.y, p, hist) ? 1u : 0u;
+      ws.p_inc += bin_exact<kDirect>(o.x, o.y, p, hist) ? 1u : 0u;
     }
   }
 }
@@ -1316,16 +1327,16 @@ __device__ __forceinline__ void orbit_credit(OrbitLane &o, WarpState &ws) {
   }
 }
 
-template <int kVar>
+template <int kVar, bool kDirect>
 __device__ __forceinline__ void orbit_step(const RenderParams &p, OrbitLane &o, WarpState &ws,
                                            const Sink &hist) {
   BUDDHA_ZSTEP(o.x, o.y, o.cx, o.cy);
-  orbit_bin<kVar>(p, o, ws, hist);
+  orbit_bin<kVar, kDirect>(p, o, ws, hist);
   o.n -= o.act ? 1 : 0;
   o.act = o.act && ((kVar & kVarFused) ? (o.n & ((1 << kOrbStepBits) - 1)) : o.n) != 0;
 }
 
-template <int kVar>
+template <int kVar, bool kDirect>
 __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                             const Sink &hist) {
   OrbitLane o = {false, 0.0, 0.0, 0.0, 0.0, 0, 0u};
@@ -1346,8 +1357,8 @@ __device__ __forceinline__ void orbit_phase(const RenderParams &p, WarpQueues &q
     }
     unsigned am = __ballot_sync(kFull, o.act);
     if (__popc(am) < kOrbExit) break;
-    orbit_step<kVar>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
-    orbit_step<kVar>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
+    orbit_step<kVar, kDirect>(p, o, ws, hist);  // two steps per refill check: orbits are >= 20 steps long on
+    orbit_step<kVar, kDirect>(p, o, ws, hist);  // every BASELINE workload, a finished lane idles for one step
   }
   orbit_credit<kVar>(o, ws);
   if (__ballot_sync(kFull, o.act)) push_z<kOrb>(q, ws.orb_n, o.act, o.cx, o.cy, o.x, o.y, o.n);
@@ -1443,7 +1454,7 @@ render_persistent_kernel(RenderParams p, uint32_t *__restrict__ hist,
       dry1 = dry && ws.t0_n == 0;
       const bool dry2 = dry1 && ws.t2_n == 0, dry3 = dry2 && ws.late_n == 0;
       if (ws.orb_n >= 32 || (ws.orb_n >= kOrbExit && ws.late_n + ws.orb_n > kZJoint)) {
-        orbit_phase<kVar>(p, q, ws, sink);
+        orbit_phase<kVar, kMaxReg == kRegsWide>(p, q, ws, sink);  // (tiled contexts take the lean build)
         continue;
       }
       if (ws.late_n >= 32 || ws.late_n + ws.orb_n > kZJoint || (dry2 && ws.late_n > 0)) {
@@ -1594,7 +1605,7 @@ orbit_drain_kernel(RenderParams p, uint32_t *__restrict__ hist,
       BUDDHA_ZSTEP(x, y, cx, cy);
       if (sub == k) { o.x = x; o.y = y; }
     }
-    orbit_bin<kVar>(p, o, ws, sink);
+    orbit_bin<kVar, false>(p, o, ws, sink);
     orbit_credit<kVar>(o, ws);
     n -= g;
   }

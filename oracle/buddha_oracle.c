@@ -399,18 +399,17 @@ int oracle_bin_reference(const oracle_dims *d, double re, double im, int64_t *in
   return bin_point(re, im, d, index);
 }
 
-typedef struct { double inv_half, c0_lo, c0_hi; int ok; } fast_axis;
+typedef struct { double inv_half, c0; int ok; } fast_axis;
 
 /* make_fast_bin of csrc/buddha_api.cu */
 static fast_axis make_fast_axis(double min_v, double delta, int n) {
-  fast_axis f = {0, 0, 0, 0};
+  fast_axis f = {0, 0, 0};
   double inv = 1.0 / delta;
   if (!(inv > 0.0) || !isfinite(inv)) return f;
   if (n > (1 << 19)) return f;
   if (!(fabs(min_v) * inv < 0x1p36)) return f;
   long double base = (long double)0x1.8p40 - (long double)min_v * (long double)inv;
-  f.c0_hi = (double)(base + (long double)0x1p-11);
-  f.c0_lo = (double)(base - (long double)0x1p-11);
+  f.c0 = (double)(base + (long double)0x1p-11);
   f.inv_half = inv * 0.5;
   f.ok = 1;
   return f;
@@ -425,13 +424,15 @@ int oracle_bin_fast(const oracle_dims *d, double re, double im, int64_t *index, 
   *took_exact = 0;
   if (!fr.ok || !fi.ok) return -1;
   double x2 = re * 2.0, y2 = im * 2.0;
-  double tch = FMA(x2, fr.inv_half, fr.c0_hi), tcl = FMA(x2, fr.inv_half, fr.c0_lo);
-  double trh = FMA(y2, fi.inv_half, fi.c0_hi), trl = FMA(y2, fi.inv_half, fi.c0_lo);
+  /* orbit_bin of csrc/buddha_kernels.cuh: one rounding per axis on the upper side of the
+   * quotient, T - 2^-10 < Q < T; outside the binade = outside the canvas; a fraction below 2^-10
+   * (none of the bits 0xffc set) = too close to a pixel boundary: the reference arithmetic decides */
+  double tc = FMA(x2, fr.inv_half, fr.c0), tr = FMA(y2, fi.inv_half, fi.c0);
   const uint32_t H0 = 0x42780000u;
-  if (hi32(tch) != H0 || hi32(trh) != H0) return 0;
-  uint32_t ch = lo32(tch), cl = lo32(tcl), rh = lo32(trh), rl = lo32(trl);
-  int same = ((((ch ^ cl) | (rh ^ rl)) >> 12) == 0u) && hi32(tcl) == H0 && hi32(trl) == H0;
-  if (!same) {
+  if (hi32(tc) != H0 || hi32(tr) != H0) return 0;
+  uint32_t ch = lo32(tc), rh = lo32(tr);
+  int clear = ((ch & 0xffcu) != 0u) && ((rh & 0xffcu) != 0u);
+  if (!clear) {
     *took_exact = 1;
     return bin_point(x2 * 0.5, y2 * 0.5, d, index);
   }

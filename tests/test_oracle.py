@@ -118,8 +118,9 @@ CANVASES = [(1000, 1000, (-2.0, 2.0, -2.0, 2.0)), (20000, 20000, (-2.0, 2.0, -2.
 
 @pytest.mark.parametrize("w,h,canvas", CANVASES)
 def test_division_free_binning_is_bit_identical(oracle, w, h, canvas):
-    """bin_point's two-rounding test either reproduces trunc(rn((v-min)/delta)) or defers to the
-    IEEE division -- including on exact pixel boundaries and their floating-point neighbours."""
+    """orbit_bin's one-rounding test (T = rn(quotient + 2^-11) on a 2^-12 grid, T - 2^-10 < Q < T)
+    either reproduces trunc(rn((v-min)/delta)) or defers to the IEEE division -- including on exact
+    pixel boundaries, their floating-point neighbours, and the edges of the deferred sliver."""
     d = oracle.make_dims(w, h, canvas[0], canvas[1], canvas[2], canvas[3])
     rng = np.random.default_rng(w * 31 + h)
     n = 400_000
@@ -135,6 +136,17 @@ def test_division_free_binning_is_bit_identical(oracle, w, h, canvas):
     bad, exact, inside = oracle.check_fast_bin(d, pts)
     assert bad == 0
     assert inside > 0 and exact > 0
+    # the edges of the sliver: 2^-12 ... 2^-9 of a pixel on either side of a boundary, +- 1 ulp
+    edge = []
+    for k in (-9, -10, -11, -12):
+        for sign in (1.0, -1.0):
+            ex = bx + sign * 2.0 ** k * d.delta_real
+            ey = by + sign * 2.0 ** k * d.delta_imag
+            for fx in (ex, np.nextafter(ex, np.inf), np.nextafter(ex, -np.inf)):
+                edge.append(np.stack([fx, ey], axis=1))
+                edge.append(np.stack([fx, rng.uniform(canvas[2], canvas[3], size=q)], axis=1))
+    bad3, _, inside3 = oracle.check_fast_bin(d, np.concatenate(edge))
+    assert bad3 == 0 and inside3 > 0
     # ordinary interior points almost never need the division
     bad2, exact2, inside2 = oracle.check_fast_bin(d, pts[3 * q:])
     assert bad2 == 0 and exact2 <= 0.01 * inside2 + 50
