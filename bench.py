@@ -271,49 +271,58 @@ def reference_arm(args, wl, rank):
 # ---- roofline model --------------------------------------------------------------------------
 # FP64-pipe warp instructions the render kernel EXECUTES, as lane-instructions per unit of work,
 # calibrated against ncu (executed DFMA / DMUL / DADD / DSETP of render_persistent_kernel from the
-# source pages of `ncu --set full` captures over 2^30-sample launches, profiles/r02_summary.md):
-# a per candidate (the exact tiers' coordinates, cardioid/bulb test, re-computed prefixes and
-# tested steps for the 17.5 % of the candidates the FP32 pre-classification does not retire), b per
-# escape-pass iteration actually executed (4 per unchecked deep step, 7 per tested step, idle
-# lanes and rolled-back rounds included), c per recorded orbit point (step 4 + division-free
-# binning 4, at the orbit phase's lane occupancy).  Fit of the round-2 kernel: config 1 34.6
-# (model 34.6), config 2 98.4 (98.3), config 3 67.4 (66.3), config 4 82.3 (82.9) per candidate.
-FP64_MODEL = {"per_candidate": 17.0, "per_executed_iteration": 4.46, "per_orbit_point": 8.6}
+# source pages of `ncu --set full` captures over 2^30-sample launches of the final round-2 kernel,
+# profiles/r02_summary.md): a per candidate (the exact tiers' coordinates, cardioid/bulb test,
+# re-computed prefixes and tested steps for the 17.5 % of the candidates the FP32 pre-classification
+# does not retire), b per escape-pass iteration actually executed (4 per unchecked deep step, 7 per
+# tested step, idle lanes and rolled-back rounds included), c per recorded orbit point (step 4 +
+# one-rounding binning 2, the exact-binning sliver), d per candidate in the build with the cycle
+# certificate.  Fit: config 1 35.0 (model 35.0), config 2 61.7 (61.7), config 3 62.2 (62.2),
+# config 4 70.0 (70.0) per candidate.
+FP64_MODEL = {"per_candidate": 18.2, "per_executed_iteration": 4.31, "per_orbit_point": 6.2,
+              "certificate_per_candidate": 3.2}
 # All warp instructions the render kernel executes per unit of work (smsp__inst_executed of the same
-# captures: config 1 6.22, config 2 8.48, config 4 9.89 per candidate; the tiled config 3 runs 9 %
-# above the fit).  Used for the issue-port figure: on this machine an FP64 instruction holds a
-# sub-partition's issue port for two cycles and FP64-chain warps do not overlap with integer warps
-# (tools/mix_probe.cu, profiles/r02_issue_probes.txt), so
-#   cycles per candidate and sub-partition ~= warp instructions + FP64 warp instructions.
-INSTR_MODEL = {"per_candidate": 4.74, "per_executed_iteration": 0.196, "per_orbit_point": 2.02}
+# captures: config 1 5.95, config 2 7.06, config 4 9.03 per candidate; the 72-register build of the
+# tiled config 3 runs 7 % above the fit: 8.92).  Used for the issue-slot figure: a sub-partition
+# issues at most one warp instruction per cycle.
+INSTR_MODEL = {"per_candidate": 4.49, "per_executed_iteration": 0.243, "per_orbit_point": 1.52,
+               "certificate_per_candidate": 0.11, "tiled_build_factor": 1.07}
 HW_FP64_LANES = 148 * 64  # FP64 lanes of one B200: the hardware issue rate is this x the SM clock
 
 
-def fp64_lane_instr(S, cnt, scale=1.0):
+def fp64_lane_instr(S, cnt, scale=1.0, cert=False):
     m = FP64_MODEL
-    return (m["per_candidate"] * S + m["per_executed_iteration"] * cnt["executed_iters"] * scale +
+    return ((m["per_candidate"] + (m["certificate_per_candidate"] if cert else 0.0)) * S +
+            m["per_executed_iteration"] * cnt["executed_iters"] * scale +
             m["per_orbit_point"] * cnt["orbit_points"] * scale)
 
 
-def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload):
+def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload, cert=False, tiled=False):
     """roofline of the dominant kernel (render_persistent_kernel): executed FP64 lane-instructions
     per second against the in-run DFMA probe; the reference-dataflow figure of SURVEY.md 8(d)
     (14 S + 8 E + 8 P, with E what the reference would have to execute) is kept beside it."""
-    lane = fp64_lane_instr(S, cnt, scale)
+    lane = fp64_lane_instr(S, cnt, scale, cert)
     lane_ref = 14 * S + 8 * cnt["escape_iters"] * scale + 8 * cnt["orbit_points"] * scale
     hw = HW_FP64_LANES * (sm_mhz or 1965.0) * 1e6
     im = INSTR_MODEL
-    warp_instr = (im["per_candidate"] * S + im["per_executed_iteration"] * cnt["executed_iters"] * scale +
+    warp_instr = ((im["per_candidate"] + (im["certificate_per_candidate"] if cert else 0.0)) * S +
+                  im["per_executed_iteration"] * cnt["executed_iters"] * scale +
                   im["per_orbit_point"] * cnt["orbit_points"] * scale)
-    port_cycles = warp_instr + lane / 32.0           # + one more cycle per FP64 warp instruction
+    if tiled:
+        warp_instr *= im["tiled_build_factor"]
     avail_cycles = t_s * 148 * 4 * (sm_mhz or 1965.0) * 1e6
-    issue_port = {"frac": port_cycles / avail_cycles,
-                  "cycles_per_candidate_model": port_cycles / S,
+    issue_port = {"frac": warp_instr / avail_cycles,
+                  "warp_instructions_per_candidate": warp_instr / S,
                   "cycles_per_candidate_measured": avail_cycles / S,
-                  "model": "issue-port cycles per candidate = warp instructions + FP64 warp "
-                           "instructions (an FP64 instruction holds a sub-partition's issue port "
-                           "for two cycles; FP64-chain and integer warps do not overlap: "
-                           "profiles/r02_issue_probes.txt), over 148 SM x 4 sub-partitions x SM clock"}
+                  "model": "issue-slot utilisation = warp instructions the kernel executes (ncu-"
+                           "calibrated, bench.py INSTR_MODEL) over 148 SM x 4 sub-partitions x SM "
+                           "clock x time: a sub-partition issues at most one warp instruction per "
+                           "cycle (ncu smsp__issue_active of the same kernel: 71-73 %).  The kernel "
+                           "is bound by instruction issue with the half-rate integer pipe (IMAD, "
+                           "LOP3, ISETP: Philox is 84 of the ~165 cycles of a sampler batch) close "
+                           "behind; the FP64 pipe is 22-35 % busy and its dependency chains largely "
+                           "run in slots the other warps leave free (round 2: removing 57 % of the "
+                           "executed iterations gained 2 %; profiles/r02_summary.md)"}
     return {
         "bound": "fp64-pipe", "unit": "Tlane-instr/s",
         "achieved": lane / t_s / 1e12, "peak": fp64_peak / 1e12, "frac": lane / t_s / fp64_peak,
@@ -327,7 +336,8 @@ def make_roofline(S, cnt, scale, t_s, fp64_peak, sm_mhz, workload):
                        "148 SM x 64 lanes x SM clock = hw_issue_rate); MEASURED_PEAKS.json has no "
                        "FP64 figure",
         "numerator": "FP64-pipe lane-instructions the kernel executes: %.1f per candidate + %.2f "
-                     "per executed escape iteration + %.1f per orbit point (ncu-calibrated, "
+                     "per executed escape iteration + %.1f per orbit point (+ 3.2 per candidate "
+                     "with the cycle certificate; ncu-calibrated, "
                      "bench.py FP64_MODEL)" % (FP64_MODEL["per_candidate"],
                                                 FP64_MODEL["per_executed_iteration"],
                                                 FP64_MODEL["per_orbit_point"]),
@@ -599,7 +609,10 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
                         (" + ncclReduce to rank 0 (only rank 0 copies)" if world > 1 else "")},
         "clocks": clocks,
         "roofline": make_roofline(S0, cnt, scale, t_s, fp64_peak,
-                                  clocks["sm_mhz"] if clocks else None, name),
+                                  clocks["sm_mhz"] if clocks else None, name,
+                                  cert=(not channels and not tiled and m >= 8000 and
+                                        not cx.args.no_shortcut),
+                                  tiled=tiled),
     }
     res["roofline_red"] = make_red_roofline(r, cnt, scale, t_s, hist_bytes, tiled, name)
     if channels:

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B: one-rounding binning + direct-scatter build against the committed kernel; parity first.
+# A/B: leaner tiled append against the committed kernel; tiled parity tests first.
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu_bin1.txt
-bash tools/gpu_ab.sh "cfg1 cfg4 cfg3 cfg5 cfg2" "head bin1" 17179869184 2>&1 | tee gpurun_out/bin1_ab.txt
+timeout -s KILL 900 python -m pytest tests -m gpu -x -q -k "tile or tiled or fused or production or cfg3" 2>&1 | tail -3
+bash tools/gpu_ab.sh "cfg3 cfg5 cfg3_m20000" "head tile1" 17179869184 2>&1 | tee gpurun_out/tile1_ab.txt
