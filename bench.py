@@ -610,7 +610,7 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
         "clocks": clocks,
         "roofline": make_roofline(S0, cnt, scale, t_s, fp64_peak,
                                   clocks["sm_mhz"] if clocks else None, name,
-                                  cert=(not channels and not tiled and m >= 8000 and
+                                  cert=(not channels and not tiled and m >= 10000 and
                                         not cx.args.no_shortcut),
                                   tiled=tiled),
     }

@@ -927,9 +927,9 @@ constexpr int kCertPasses = 5;                   // Newton evaluations (the last
 constexpr float kCertTol = 1e-2f;
 constexpr double kCertResMax = 1e-12, kCertLam2Max = 0.998;
 #ifndef BUDDHA_CERT_MIN_IT
-#define BUDDHA_CERT_MIN_IT 8000
+#define BUDDHA_CERT_MIN_IT 10000
 #endif
-constexpr int kCertMinIt = BUDDHA_CERT_MIN_IT;   // below this -m the bit-exact search is cheaper (-m 5000: -3 %)
+constexpr int kCertMinIt = BUDDHA_CERT_MIN_IT;   // below this -m the bit-exact search is cheaper (-m 5000: -2.4 %, -m 20000: +6.5 %: break-even near 9000)
 constexpr int kCertQueue = 512;                  // queue entries per warp (host side: RenderParams::cert_cap)
 constexpr int kCertHeadroom = 32;                // entries kept free at the top (cert_phase, stage C)
 #ifndef BUDDHA_CERT_GANG

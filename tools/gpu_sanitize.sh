@@ -21,7 +21,7 @@ run(width=64, height=64, max_iterations=5, min_iterations=0, n=5000)
 run(width=64, height=48, max_iterations=400, min_iterations=20, n=1 << 16)   # privatised copies
 # round 2: the cycle certificate (queues in global memory, per-lane refill, re-injection into deep)
 os.environ["BUDDHA_CERT_QUEUE"] = "160"
-run(width=200, height=150, max_iterations=9000, min_iterations=20, n=1 << 18)
+run(width=200, height=150, max_iterations=10000, min_iterations=20, n=1 << 18)
 del os.environ["BUDDHA_CERT_QUEUE"]
 # round 2: a pipeline of tiled launches with orbit carry-over (1 MB list pool -> many launches)
 import os
