@@ -126,6 +126,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    def wait_first(self, timeout=3.0):
+        """Block until nvidia-smi has produced its first line (it can take more than a second on a
+        fresh box), so that the timed region is sampled from its start."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def mark_start(self):
         self.t_start = time.perf_counter()
 
@@ -518,7 +525,7 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
     sampler = ClockSampler(cx.local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)  # nvidia-smi needs a moment before its first line
+        sampler.wait_first()  # nvidia-smi needs a moment before its first line
     # ---- timed region: `steps` steps, device-timed per step --------------------------------
     cx.barrier()
     sampler.mark_start()
@@ -653,7 +660,7 @@ def run_strong(cx, name="cfg3_m20000", n_total=1 << 39):
     sampler = ClockSampler(cx.local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first()
     f, n = contiguous_split(0, n_total, rank, world)
     cx.barrier()
     sampler.mark_start()
@@ -743,7 +750,7 @@ def native_arm(args, wl, rank, world, local_rank):
         for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
             if name == args.workload:
                 continue
-            res = run_workload(cx, name, 0, 1, WORKLOADS[name][5], min_seconds=1.3, e2e_steps=6,
+            res = run_workload(cx, name, 0, 1, WORKLOADS[name][5], min_seconds=1.6, e2e_steps=6,
                                baselines=not args.skip_baselines)
             if res:
                 extras.append(res)
