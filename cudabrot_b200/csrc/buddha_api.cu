@@ -13,6 +13,7 @@
 //   BUDDHA_PAD_SMEM           extra dynamic shared memory per CTA (occupancy experiments)
 //   BUDDHA_NO_CARRY           drain the leftover orbits after every pipeline launch (no carry-over)
 //   BUDDHA_TILE_TRACE         print device timestamps of every pipeline launch to stderr
+//   BUDDHA_CERT_QUEUE         entries per warp of the cycle-certificate queues (512; 0 = no certificate)
 #include "../../include/buddha.h"
 #include "buddha_kernels.cuh"
 
