@@ -115,7 +115,7 @@ int oracle_rejected_scaled(double c_real, double c_imag);
 /* Reference binning (cudabrot.cu:302-314): returns 1 and the cell index if (re, im) is counted. */
 int oracle_bin_reference(const oracle_dims *d, double re, double im, int64_t *index);
 
-/* Division-free binning of bin_point (two DFMA roundings per axis); *took_exact is set when the
+/* Division-free binning of orbit_bin (one DFMA rounding per axis, on the upper side of the quotient); *took_exact is set when the
  * fast path declined and the IEEE-division path decided.  Returns -1 if the canvas does not
  * admit the fast path at all (product falls back to exact binning for every point). */
 int oracle_bin_fast(const oracle_dims *d, double re, double im, int64_t *index, int *took_exact);
