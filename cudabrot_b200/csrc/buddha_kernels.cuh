@@ -43,7 +43,15 @@ constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 // runs first, with whatever it holds).
 constexpr int kDeepCap = 63;
 constexpr int kZCap = 87, kZJoint = kZCap - 32;
-constexpr int kCCap = 94;
+// The sampler draws two candidates per lane and loop trip: twice the instruction-level parallelism
+// in the Philox chains (ten dependent multiply-xor rounds), one loop trip and one stack update for
+// both.  Config 1 +3.6 %, config 2 +3.3 %, config 4 +2.2 % (profiles/r02_sampler_two_per_lane_ab.txt;
+// BUDDHA_GEN2=0: one per lane, A/B builds).
+#ifndef BUDDHA_GEN2
+#define BUDDHA_GEN2 1
+#endif
+constexpr bool kGen2 = BUDDHA_GEN2 != 0;
+constexpr int kCCap = kGen2 ? 126 : 94;        // (t0 then holds up to 31 + 64 while t2 holds <= 31)
 constexpr int kSpillPerWarp = 32;                // a warp leaves the kernel with < 32 accepted samples
 constexpr int kDrainLong = 1024;                 // leftovers this long get a warp each, if they are few
 constexpr int kChunk = 4096;                   // granularity of launch sizes (host side)
@@ -683,6 +691,30 @@ __device__ __forceinline__ void tested_steps(double &x, double &y, double cx, do
 // `t0` as its four Philox words; the first exact tier re-derives c from them in FP64.
 constexpr float kPreRejMargin = 0.02f, kPreEscMargin = 0.05f;
 
+// The sampler's FP32 pre-classification of one candidate from its Philox words (see gen_phase).
+template <int kVar>
+__device__ __forceinline__ void gen_classify(const uint4 &r, float esc1_min, float esc2_min,
+                                             bool &rej, bool &esc1, bool &esc2) {
+  // 2c to ~1e-6: the mantissa trick turns the top 23 bits of a word into [1, 2)
+  const float cx = __fmaf_rn(__uint_as_float(0x3F800000u | (r.y >> 9)), 8.0f, -12.0f);
+  const float cy = __fmaf_rn(__uint_as_float(0x3F800000u | (r.w >> 9)), 8.0f, -12.0f);
+  const float i2 = cy * cy;
+  rej = false;
+  if constexpr ((kVar & kVarShip) == 0) {  // rejected2 in float (cudabrot.cu:284-298, :397-399)
+    const float q0 = cx - 0.5f, qq = __fmaf_rn(q0, q0, i2), sx = __fmaf_rn(q0, 2.0f, qq);
+    const float t = cx + 2.0f;
+    rej = (qq * sx < i2 - kPreRejMargin) || (__fmaf_rn(t, t, i2) < 0.25f - kPreRejMargin);
+  }
+  const float x1 = __fmaf_rn(__fmaf_rn(cx, cx, -i2), 0.5f, cx);
+  const float y1 = (kVar & kVarShip) ? __fmaf_rn(fabsf(cx), fabsf(cy), cy) : __fmaf_rn(cx, cy, cy);
+  const float n1 = __fmaf_rn(y1, y1, x1 * x1);
+  const float x2 = __fmaf_rn(__fmaf_rn(x1, x1, -y1 * y1), 0.5f, cx);
+  const float y2 = (kVar & kVarShip) ? __fmaf_rn(fabsf(x1), fabsf(y1), cy) : __fmaf_rn(x1, y1, cy);
+  const float n2 = __fmaf_rn(y2, y2, x2 * x2);
+  esc1 = !rej && n1 > esc1_min;
+  esc2 = !rej && n1 < 16.0f - kPreEscMargin && n2 > esc2_min;
+}
+
 template <int kVar>
 __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, WarpState &ws,
                                           unsigned long long *cursor,
@@ -719,34 +751,41 @@ __device__ __forceinline__ void gen_phase(const RenderParams &p, WarpQueues &q, 
       ws.chunk_off = 0;
       ws.chunk_len = (base + p.chunk <= p.end) ? p.chunk : (uint32_t)(p.end - base);
     }
+    if constexpr (kGen2) {
+      // two independent candidates per lane: twice the instruction-level parallelism in the Philox
+      // chains, one loop trip and one stack update for both
+      const uint32_t o0 = ws.chunk_off + lane, o1 = o0 + 32u;
+      const bool valid0 = o0 < ws.chunk_len, valid1 = o1 < ws.chunk_len;
+      ws.chunk_off += 64;
+      const uint4 r0 = philox4x32_10(ws.chunk_base + o0, p);
+      const uint4 r1 = philox4x32_10(ws.chunk_base + o1, p);
+      bool rej0, e10, e20, rej1, e11, e21;
+      gen_classify<kVar>(r0, esc1_min, esc2_min, rej0, e10, e20);
+      gen_classify<kVar>(r1, esc1_min, esc2_min, rej1, e11, e21);
+      ws.n_rej += ((valid0 && rej0) ? 1u : 0u) + ((valid1 && rej1) ? 1u : 0u);
+      ws.steps += ((valid0 && e10) ? 1u : 0u) + ((valid1 && e11) ? 1u : 0u);
+      ws.steps += ((valid0 && e20) ? 2u : 0u) + ((valid1 && e21) ? 2u : 0u);
+      const bool keep0 = valid0 && !(rej0 || e10 || e20), keep1 = valid1 && !(rej1 || e11 || e21);
+      const unsigned m0 = __ballot_sync(kFull, keep0), m1 = __ballot_sync(kFull, keep1);
+      const int s0 = ws.t0_n + __popc(m0 & lanemask_lt());
+      const int s1 = ws.t0_n + __popc(m0) + __popc(m1 & lanemask_lt());
+      ws.t0_n += __popc(m0) + __popc(m1);
+      if (keep0) q.c_w[slot_of<kT0, kCCap>(s0)] = r0;
+      if (keep1) q.c_w[slot_of<kT0, kCCap>(s1)] = r1;
+    } else {
     const uint32_t o = ws.chunk_off + lane;
     const bool valid = o < ws.chunk_len;
     ws.chunk_off += 32;
     const uint4 r = philox4x32_10(ws.chunk_base + o, p);
-    // 2c to ~1e-6: the mantissa trick turns the top 23 bits of a word into [1, 2)
-    const float cx = __fmaf_rn(__uint_as_float(0x3F800000u | (r.y >> 9)), 8.0f, -12.0f);
-    const float cy = __fmaf_rn(__uint_as_float(0x3F800000u | (r.w >> 9)), 8.0f, -12.0f);
-    const float i2 = cy * cy;
-    bool rej = false;
-    if constexpr ((kVar & kVarShip) == 0) {  // rejected2 in float (cudabrot.cu:284-298, :397-399)
-      const float q0 = cx - 0.5f, qq = __fmaf_rn(q0, q0, i2), sx = __fmaf_rn(q0, 2.0f, qq);
-      const float t = cx + 2.0f;
-      rej = (qq * sx < i2 - kPreRejMargin) || (__fmaf_rn(t, t, i2) < 0.25f - kPreRejMargin);
-    }
-    const float x1 = __fmaf_rn(__fmaf_rn(cx, cx, -i2), 0.5f, cx);
-    const float y1 = (kVar & kVarShip) ? __fmaf_rn(fabsf(cx), fabsf(cy), cy) : __fmaf_rn(cx, cy, cy);
-    const float n1 = __fmaf_rn(y1, y1, x1 * x1);
-    const float x2 = __fmaf_rn(__fmaf_rn(x1, x1, -y1 * y1), 0.5f, cx);
-    const float y2 = (kVar & kVarShip) ? __fmaf_rn(fabsf(x1), fabsf(y1), cy) : __fmaf_rn(x1, y1, cy);
-    const float n2 = __fmaf_rn(y2, y2, x2 * x2);
-    const bool esc1 = !rej && n1 > esc1_min;
-    const bool esc2 = !rej && n1 < 16.0f - kPreEscMargin && n2 > esc2_min;
+    bool rej, esc1, esc2;
+    gen_classify<kVar>(r, esc1_min, esc2_min, rej, esc1, esc2);
     ws.n_rej += (valid && rej) ? 1u : 0u;
     ws.steps += (valid && esc1) ? 1u : 0u;
     ws.steps += (valid && esc2) ? 2u : 0u;
     const bool keep = valid && !(rej || esc1 || esc2);
     const int slot = slot_of<kT0, kCCap>(push_slot(ws.t0_n, keep));
     if (keep) q.c_w[slot] = r;
+    }
   }
   __syncwarp();
 }
