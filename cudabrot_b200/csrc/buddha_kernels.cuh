@@ -36,9 +36,11 @@ namespace buddha {
 constexpr int kWarpsPerCta = BUDDHA_WARPS_PER_CTA;
 constexpr int kCtasPerSm = BUDDHA_CTAS_PER_SM;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-// Work stacks (entries).  A phase pops at most 32 entries and pushes at most 32, and runs only
-// while its targets hold < 32, so no stack exceeds 63.  `late` and `orb` share one array and grow
-// towards each other, and so do `t0` and `t2`: t0 + t2 <= 63 + 31, and late + orb <= kZJoint + 32
+// Work stacks (entries).  A phase pops at most 32 entries and pushes at most 32 (the sampler: 64
+// into t0), and runs only while its targets hold < 32, so no stack exceeds 63 (t0: 95).  `late` and
+// `orb` share one array and grow towards each other, and so do `t0` and `t2`: t0 + t2 <= 95 + 31
+// (the sampler runs only while t2 < 32, the first tier leaves t0 <= 63 when it fills t2 to <= 63),
+// and late + orb <= kZJoint + 32
 // because every phase that pushes to them starts only while late + orb <= kZJoint (else `late`
 // runs first, with whatever it holds).
 constexpr int kDeepCap = 63;
