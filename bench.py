@@ -518,6 +518,11 @@ def run_workload(cx, name, steps, warmup, per_gpu, min_seconds=0.0, e2e_steps=No
         t_first = r.last_render_ms() * per_gpu / n
     if steps == 0:
         steps = cx.bcast_int(max(2, int(np.ceil(min_seconds * 1e3 / max(t_first, 1e-3)))))
+    if world > 1:
+        # warm-up of the one collective too: NCCL sets up its buffers for a new message size at the
+        # first call (a 1.2 GB reduce once took 143 ms instead of 17)
+        dist.reduce(hist_t, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
     r.clear()
     r.reset_counters()
     fp64_peak = r.probe_fp64_peak()
